@@ -1,0 +1,823 @@
+// Host side of the C ABI (include/ira.h): context, HBM workspace, CSR build, the IRLS / PCG
+// drivers, NCCL plumbing.  The loop structure restates irotavg::irls (ral/l1_irls.cpp:559-752);
+// the SuiteSparseQR least-squares solve (ral/l1_irls.cpp:536-556) is replaced by Jacobi-PCG on
+// the weighted normal equations.  No CPU compute path exists here.
+#include "../../include/ira.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cub/device/device_radix_sort.cuh>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "ira_kernels.cuh"
+
+using namespace ira;
+
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+enum KClass { KC_RESIDUAL = 0, KC_RHS, KC_SPMV, KC_CGVEC, KC_WEIGHTS, KC_UPDATE, KC_COMM, KC_OTHER, KC_N };
+
+// NCCL resolved at run time so that the single-GPU library has no link-time dependency on it.
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) return false;
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && AllReduce && CommDestroy && GetErrorString;
+  }
+};
+NcclApi g_nccl;
+
+}  // namespace
+
+struct ira_context {
+  ira_options opt;
+  int device = 0;
+  int sms = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  // problem
+  bool uploaded = false;
+  int64_t m = 0, m_pad = 0;
+  int n = 0, f = 0, nnz = 0, lpr = 8;
+
+  DevBuf I, QQ, weights, wres, Q, Q0, stage;
+  DevBuf rowptr, ent_col, ent_eid, ent_w2, keys, vals, cubtmp;
+  DevBuf X, R, Z, P, AP, B, diag, dinv;
+  DevBuf ctl, partials, bad, flush;
+  Ctl* h_ctl = nullptr;  // pinned
+
+  // comm
+  ncclComm_t comm = nullptr;
+
+  // profiling
+  struct Span { int cls; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  int launches = 0;
+  int prev_cg = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+#define IRA_CUDA(h, expr)                                                                    \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      char buf__[512];                                                                        \
+      snprintf(buf__, sizeof buf__, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,      \
+               cudaGetErrorString(e__));                                                      \
+      (h)->err = buf__;                                                                       \
+      return IRA_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+#define IRA_TRY(expr)                             \
+  do {                                            \
+    ira_status s__ = (expr);                      \
+    if (s__ != IRA_OK) return s__;                \
+  } while (0)
+
+namespace {
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+cudaEvent_t prof_event(ira_context* h) {
+  if (h->ev_used == h->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev_pool.push_back(e);
+  }
+  return h->ev_pool[h->ev_used++];
+}
+struct ProfScope {
+  ira_context* h; int idx = -1;
+  ProfScope(ira_context* h_, int cls) : h(h_) {
+    if (h->opt.profile) {
+      ira_context::Span s{cls, prof_event(h), prof_event(h)};
+      cudaEventRecord(s.a, h->stream);
+      h->spans.push_back(s);
+      idx = (int)h->spans.size() - 1;
+    }
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(h->spans[idx].b, h->stream); }
+};
+
+void prof_collect(ira_context* h, ira_stats* st) {
+  if (!h->opt.profile) return;
+  cudaStreamSynchronize(h->stream);
+  double t[KC_N] = {0}; int c[KC_N] = {0};
+  for (auto& s : h->spans) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s.a, s.b);
+    t[s.cls] += ms; c[s.cls] += 1;
+  }
+  h->spans.clear();
+  h->ev_used = 0;
+  if (st) {
+    st->t_residual_ms = t[KC_RESIDUAL]; st->n_residual = c[KC_RESIDUAL];
+    st->t_rhs_ms = t[KC_RHS]; st->n_rhs = c[KC_RHS];
+    st->t_spmv_ms = t[KC_SPMV]; st->n_spmv = c[KC_SPMV];
+    st->t_cgvec_ms = t[KC_CGVEC]; st->n_cgvec = c[KC_CGVEC];
+    st->t_weights_ms = t[KC_WEIGHTS]; st->n_weights = c[KC_WEIGHTS];
+    st->t_update_ms = t[KC_UPDATE]; st->n_update = c[KC_UPDATE];
+    st->t_comm_ms = t[KC_COMM]; st->n_comm = c[KC_COMM];
+  }
+}
+
+int grid_nodes(const ira_context* h, int n, int threads = 256) {
+  return std::max(1, std::min(cdiv(n, threads), h->sms * 8));
+}
+int grid_rows(const ira_context* h, int n, int lpr) {
+  const int64_t warps = cdiv(n, 32 / lpr);
+  return std::max(1, std::min(cdiv(warps * 32, 256), h->sms * 8));
+}
+
+ira_status launch_check(ira_context* h, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    h->err = std::string(what) + " launch failed: " + cudaGetErrorString(e);
+    return IRA_ERR_CUDA;
+  }
+  h->launches++;
+  return IRA_OK;
+}
+
+int pick_lpr(const ira_context* h) {
+  int l = h->opt.lanes_per_row;
+  if (l >= 2 && l <= 32 && (l & (l - 1)) == 0) return l;
+  const double avg = h->n > 0 ? (double)h->nnz / h->n : 0.0;
+  int v = 4;
+  while (v < 32 && v * 3 < avg) v *= 2;
+  return v;
+}
+
+// ---- kernel launch wrappers ------------------------------------------------------------------
+ira_status run_residual(ira_context* h, const double4* Qsrc, int store_theta) {
+  if (h->m == 0) return IRA_OK;
+  ProfScope ps(h, KC_RESIDUAL);
+  const int ntiles = (int)(h->m_pad / kResTile);
+  const int grid = std::min(ntiles, h->sms * 8);
+  k_residual<<<grid, kResTile, 0, h->stream>>>(h->I.as<int2>(), h->QQ.as<double>(), h->m_pad,
+                                               h->weights.as<double>(), Qsrc, h->wres.as<double4>(),
+                                               h->m, ntiles, store_theta);
+  return launch_check(h, "k_residual");
+}
+
+template <int LPR>
+ira_status run_rhs_t(ira_context* h) {
+  k_rhs_diag<LPR><<<grid_rows(h, h->n, LPR), 256, 0, h->stream>>>(
+      h->rowptr.as<int>(), h->ent_eid.as<int>(), h->wres.as<double4>(), h->ent_w2.as<double>(),
+      h->B.as<double4>(), h->diag.as<double>(), h->n);
+  return launch_check(h, "k_rhs_diag");
+}
+ira_status run_rhs(ira_context* h) {
+  ProfScope ps(h, KC_RHS);
+  switch (h->lpr) {
+    case 2: return run_rhs_t<2>(h);
+    case 4: return run_rhs_t<4>(h);
+    case 8: return run_rhs_t<8>(h);
+    case 16: return run_rhs_t<16>(h);
+    default: return run_rhs_t<32>(h);
+  }
+}
+
+template <int LPR>
+ira_status run_spmv_t(ira_context* h, bool fuse) {
+  const int grid = grid_rows(h, h->n, LPR);
+  if (fuse)
+    k_spmv<LPR, true><<<grid, 256, 0, h->stream>>>(h->rowptr.as<int>(), h->ent_col.as<int>(),
+                                                   h->ent_w2.as<double>(), h->P.as<double4>(),
+                                                   h->AP.as<double4>(), h->n, h->ctl.as<Ctl>(),
+                                                   h->partials.as<double>());
+  else
+    k_spmv<LPR, false><<<grid, 256, 0, h->stream>>>(h->rowptr.as<int>(), h->ent_col.as<int>(),
+                                                    h->ent_w2.as<double>(), h->P.as<double4>(),
+                                                    h->AP.as<double4>(), h->n, h->ctl.as<Ctl>(),
+                                                    h->partials.as<double>());
+  return launch_check(h, "k_spmv");
+}
+ira_status run_spmv(ira_context* h, bool fuse) {
+  ProfScope ps(h, KC_SPMV);
+  switch (h->lpr) {
+    case 2: return run_spmv_t<2>(h, fuse);
+    case 4: return run_spmv_t<4>(h, fuse);
+    case 8: return run_spmv_t<8>(h, fuse);
+    case 16: return run_spmv_t<16>(h, fuse);
+    default: return run_spmv_t<32>(h, fuse);
+  }
+}
+
+ira_status allreduce_f64(ira_context* h, double* buf, size_t count) {
+  if (h->opt.world_size <= 1) return IRA_OK;
+  if (!h->comm) { h->err = "world_size > 1 but ira_comm_init was not called"; return IRA_ERR_COMM; }
+  ProfScope ps(h, KC_COMM);
+  ncclResult_t r = g_nccl.AllReduce(buf, buf, count, ncclFloat64, ncclSum, h->comm, h->stream);
+  if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r); return IRA_ERR_COMM; }
+  return IRA_OK;
+}
+
+ira_status run_cg_init(ira_context* h) {
+  ProfScope ps(h, KC_CGVEC);
+  k_cg_init<<<grid_nodes(h, h->n, kRedThreads), kRedThreads, 0, h->stream>>>(
+      h->B.as<double4>(), h->diag.as<double>(), h->dinv.as<double>(), h->X.as<double4>(),
+      h->R.as<double4>(), h->Z.as<double4>(), h->P.as<double4>(), h->n, h->ctl.as<Ctl>(),
+      h->partials.as<double>());
+  return launch_check(h, "k_cg_init");
+}
+
+ira_status run_cg_iteration(ira_context* h) {
+  const bool sharded = h->opt.world_size > 1;
+  IRA_TRY(run_spmv(h, !sharded));
+  if (sharded) {
+    IRA_TRY(allreduce_f64(h, h->AP.as<double>(), (size_t)h->n * 4));
+    ProfScope ps(h, KC_CGVEC);
+    k_cg_dot_pap<<<grid_nodes(h, h->n, kRedThreads), kRedThreads, 0, h->stream>>>(
+        h->P.as<double4>(), h->AP.as<double4>(), h->n, h->ctl.as<Ctl>(), h->partials.as<double>());
+    IRA_TRY(launch_check(h, "k_cg_dot_pap"));
+  }
+  {
+    ProfScope ps(h, KC_CGVEC);
+    k_cg_update<<<grid_nodes(h, h->n, kRedThreads), kRedThreads, 0, h->stream>>>(
+        h->X.as<double4>(), h->R.as<double4>(), h->Z.as<double4>(), h->P.as<double4>(),
+        h->AP.as<double4>(), h->dinv.as<double>(), h->n, h->ctl.as<Ctl>(), h->partials.as<double>());
+    IRA_TRY(launch_check(h, "k_cg_update"));
+  }
+  {
+    ProfScope ps(h, KC_CGVEC);
+    k_cg_p<<<grid_nodes(h, h->n), 256, 0, h->stream>>>(h->P.as<double4>(), h->Z.as<double4>(), h->n,
+                                                       h->ctl.as<Ctl>());
+    IRA_TRY(launch_check(h, "k_cg_p"));
+  }
+  return IRA_OK;
+}
+
+ira_status fetch_ctl(ira_context* h) {
+  IRA_CUDA(h, cudaMemcpyAsync(h->h_ctl, h->ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IRA_OK;
+}
+
+// One linear step: Jacobi-PCG on A^T D^2 A X = A^T D^2 w, x0 = 0 (replaces ls_solve, :536-556).
+ira_status solve_pcg(ira_context* h, int* iters_out, double* relres_out, int* hit_max) {
+  IRA_TRY(run_rhs(h));
+  IRA_TRY(allreduce_f64(h, h->B.as<double>(), (size_t)h->n * 4));
+  IRA_TRY(allreduce_f64(h, h->diag.as<double>(), (size_t)h->n));
+  IRA_TRY(run_cg_init(h));
+  const int cap = std::max(0, h->opt.cg_max_iters);
+  const int every = std::max(1, h->opt.cg_check_every);
+  int issued = 0;
+  bool first = true;
+  for (;;) {
+    int chunk = every;
+    if (first && h->prev_cg > every) chunk = h->prev_cg - every / 2;   // solves of consecutive IRLS
+    first = false;                                                     // iterations need similar counts
+    chunk = std::min(chunk, cap - issued);
+    for (int c = 0; c < chunk; ++c) IRA_TRY(run_cg_iteration(h));
+    issued += chunk;
+    IRA_TRY(fetch_ctl(h));
+    if (h->h_ctl->done || issued >= cap) break;
+  }
+  const Ctl& c = *h->h_ctl;
+  double rel = 0.0;
+  bool conv = true;
+  for (int k = 0; k < 3; ++k) {
+    if (c.bnorm2[k] > 0.0) rel = std::max(rel, sqrt(c.rnorm2[k] / c.bnorm2[k]));
+    if (!(c.rnorm2[k] <= c.rtol2 * c.bnorm2[k])) conv = false;
+  }
+  *iters_out = c.cg_iters;
+  *relres_out = rel;
+  *hit_max = conv ? 0 : 1;
+  h->prev_cg = c.cg_iters;
+  return IRA_OK;
+}
+
+ira_status alloc_problem(ira_context* h, int64_t m, int n) {
+  const int64_t m_pad = std::max<int64_t>(kResTile, ((m + kResTile - 1) / kResTile) * kResTile);
+  h->m = m; h->m_pad = m_pad; h->n = n;
+  IRA_CUDA(h, h->I.reserve(sizeof(int2) * m_pad));
+  IRA_CUDA(h, h->QQ.reserve(sizeof(double) * 4 * m_pad));
+  IRA_CUDA(h, h->weights.reserve(sizeof(double) * m_pad));
+  IRA_CUDA(h, h->wres.reserve(sizeof(double4) * m_pad));
+  IRA_CUDA(h, h->Q.reserve(sizeof(double4) * (size_t)std::max(n, 1)));
+  IRA_CUDA(h, h->Q0.reserve(sizeof(double4) * (size_t)std::max(n, 1)));
+  IRA_CUDA(h, h->stage.reserve(sizeof(double) * 4 * (size_t)std::max<int64_t>(std::max<int64_t>(n, m), 1)));
+  IRA_CUDA(h, h->rowptr.reserve(sizeof(int) * ((size_t)n + 1)));
+  IRA_CUDA(h, h->ent_col.reserve(sizeof(int) * (size_t)std::max<int64_t>(2 * m, 1)));
+  IRA_CUDA(h, h->ent_eid.reserve(sizeof(int) * (size_t)std::max<int64_t>(2 * m, 1)));
+  IRA_CUDA(h, h->ent_w2.reserve(sizeof(double) * (size_t)std::max<int64_t>(2 * m, 1)));
+  IRA_CUDA(h, h->keys.reserve(sizeof(int) * (size_t)std::max<int64_t>(4 * m, 1)));
+  IRA_CUDA(h, h->vals.reserve(sizeof(int) * (size_t)std::max<int64_t>(4 * m, 1)));
+  for (DevBuf* b : {&h->X, &h->R, &h->Z, &h->P, &h->AP, &h->B})
+    IRA_CUDA(h, b->reserve(sizeof(double4) * (size_t)std::max(n, 1)));
+  IRA_CUDA(h, h->diag.reserve(sizeof(double) * (size_t)std::max(n, 1)));
+  IRA_CUDA(h, h->dinv.reserve(sizeof(double) * (size_t)std::max(n, 1)));
+  return IRA_OK;
+}
+
+ira_status build_csr(ira_context* h) {
+  const int64_t m = h->m;
+  const int n = h->n;
+  IRA_CUDA(h, cudaMemsetAsync(h->bad.p, 0, sizeof(int), h->stream));
+  int* keys_in = h->keys.as<int>();
+  int* keys_out = keys_in + 2 * m;
+  int* vals_in = h->vals.as<int>();
+  int* vals_out = vals_in + 2 * m;
+  if (m > 0) {
+    k_csr_keys<<<std::min(cdiv(m, 256), h->sms * 16), 256, 0, h->stream>>>(h->I.as<int2>(), m, n, h->f,
+                                                                         keys_in, vals_in, h->bad.as<int>());
+    IRA_TRY(launch_check(h, "k_csr_keys"));
+    int end_bit = 1;
+    while ((1ll << end_bit) <= (int64_t)n) ++end_bit;      // keys are in [0, n]
+    size_t tmp_bytes = 0;
+    IRA_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out,
+                                                (int)(2 * m), 0, end_bit, h->stream));
+    IRA_CUDA(h, h->cubtmp.reserve(tmp_bytes));
+    IRA_CUDA(h, cub::DeviceRadixSort::SortPairs(h->cubtmp.p, tmp_bytes, keys_in, keys_out, vals_in, vals_out,
+                                                (int)(2 * m), 0, end_bit, h->stream));
+    h->launches += 4;
+  }
+  k_csr_finalize<<<std::max(1, std::min(cdiv(2 * m + 1, 256), h->sms * 16)), 256, 0, h->stream>>>(
+      keys_out, vals_out, h->I.as<int2>(), 2 * m, n, h->rowptr.as<int>(), h->ent_col.as<int>(),
+      h->ent_eid.as<int>());
+  IRA_TRY(launch_check(h, "k_csr_finalize"));
+  int host[2] = {0, 0};
+  IRA_CUDA(h, cudaMemcpyAsync(&host[0], h->rowptr.as<int>() + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  IRA_CUDA(h, cudaMemcpyAsync(&host[1], h->bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (host[1]) { h->err = "edge endpoint out of range [0, n_total)"; return IRA_ERR_INVALID_ARG; }
+  h->nnz = host[0];
+  h->lpr = pick_lpr(h);
+  return IRA_OK;
+}
+
+ira_status upload_Q(ira_context* h, const double* Q, int64_t ld_q, DevBuf& dst) {
+  const int n = h->n;
+  if (n == 0) return IRA_OK;
+  IRA_CUDA(h, cudaMemcpy2DAsync(h->stage.p, sizeof(double) * n, Q, sizeof(double) * ld_q, sizeof(double) * n,
+                                4, cudaMemcpyHostToDevice, h->stream));
+  k_colmajor_to_aos4<<<grid_nodes(h, n), 256, 0, h->stream>>>(h->stage.as<double>(), n, dst.as<double4>(), n);
+  return launch_check(h, "k_colmajor_to_aos4");
+}
+
+ira_status check_args(ira_context* h, int64_t m, int64_t n_total, int32_t f, const void* I, const void* QQ,
+                      int64_t ld_qq, const void* Q, int64_t ld_q) {
+  if (!h) return IRA_ERR_INVALID_ARG;
+  auto bad = [&](const char* why) { h->err = why; return IRA_ERR_INVALID_ARG; };
+  if (m < 0 || n_total < 0) return bad("negative size");
+  if (m > (1ll << 30) - 1 || n_total > std::numeric_limits<int>::max() - 2) return bad("problem too large for int32 indices");
+  if (f < 1) return bad("f < 1: at least one rotation must be fixed (ral/l1_irls.cpp:917)");
+  if (f > n_total) return bad("f > n_total");
+  if (m > 0 && (!I || !QQ)) return bad("null edge arrays");
+  if (n_total > 0 && !Q) return bad("null Q");
+  if (ld_qq < m || ld_q < n_total) return bad("leading dimension smaller than row count");
+  return IRA_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int32_t ira_abi_version(void) { return IRA_ABI_VERSION; }
+
+int32_t ira_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* ira_status_string(ira_status s) {
+  switch (s) {
+    case IRA_OK: return "ok";
+    case IRA_ERR_INVALID_ARG: return "invalid argument";
+    case IRA_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (there is no CPU path)";
+    case IRA_ERR_CUDA: return "CUDA error";
+    case IRA_ERR_COMM: return "NCCL / communicator error";
+    case IRA_ERR_UNKNOWN_COST: return "Unknown cost!!";
+    case IRA_ERR_NOT_UPLOADED: return "no problem uploaded";
+    case IRA_ERR_NONFINITE: return "non-finite score";
+    case IRA_ERR_NOT_SPANNING: return "Relative rotations DO NOT SPAN all the nodes in the VIEW GRAPH";
+  }
+  return "unknown status";
+}
+
+const char* ira_last_error(ira_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+ira_status ira_options_default(ira_options* o) {
+  if (!o) return IRA_ERR_INVALID_ARG;
+  memset(o, 0, sizeof *o);
+  o->device = -1;
+  o->cg_max_iters = 20000;
+  o->cg_rtol = 1e-10;
+  o->cg_check_every = 16;
+  o->lanes_per_row = 0;
+  o->world_size = 1;
+  o->rank = 0;
+  o->profile = 0;
+  return IRA_OK;
+}
+
+ira_status ira_create(ira_handle* out, const ira_options* opt) {
+  if (!out) return IRA_ERR_INVALID_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return IRA_ERR_NO_DEVICE; }
+  ira_context* h = new ira_context();
+  if (opt) h->opt = *opt; else ira_options_default(&h->opt);
+  if (h->opt.world_size < 1) h->opt.world_size = 1;
+  int dev = h->opt.device;
+  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+  if (dev >= ndev) { delete h; return IRA_ERR_NO_DEVICE; }
+  cudaDeviceProp prop;
+  if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+    cudaGetLastError();
+    delete h;
+    return IRA_ERR_NO_DEVICE;   // kernels are built for sm_100a only
+  }
+  h->device = dev;
+  h->sms = prop.multiProcessorCount;
+  bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaMallocHost((void**)&h->h_ctl, sizeof(Ctl)) == cudaSuccess;
+  ok = ok && h->ctl.reserve(sizeof(Ctl)) == cudaSuccess;
+  ok = ok && h->partials.reserve(sizeof(double) * 8 * kRedMaxBlocks) == cudaSuccess;
+  ok = ok && h->bad.reserve(sizeof(int)) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); ira_destroy(h); return IRA_ERR_CUDA; }
+  *out = h;
+  return IRA_OK;
+}
+
+ira_status ira_destroy(ira_handle h) {
+  if (!h) return IRA_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (DevBuf* b : {&h->I, &h->QQ, &h->weights, &h->wres, &h->Q, &h->Q0, &h->stage, &h->rowptr, &h->ent_col,
+                    &h->ent_eid, &h->ent_w2, &h->keys, &h->vals, &h->cubtmp, &h->X, &h->R, &h->Z, &h->P,
+                    &h->AP, &h->B, &h->diag, &h->dinv, &h->ctl, &h->partials, &h->bad, &h->flush})
+    b->release();
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
+  if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return IRA_OK;
+}
+
+ira_status ira_problem_upload(ira_handle h, int64_t m, int64_t n_total, int32_t f, const int32_t* I_pairs,
+                              const double* QQ, int64_t ld_qq, const double* Q0, int64_t ld_q) {
+  IRA_TRY(check_args(h, m, n_total, f, I_pairs, QQ, ld_qq, Q0, ld_q));
+  IRA_CUDA(h, cudaSetDevice(h->device));
+  h->uploaded = false;
+  h->f = f;
+  IRA_TRY(alloc_problem(h, m, (int)n_total));
+  const int64_t mp = h->m_pad;
+  // padded tails are zero so that whole 256-edge tiles can always be bulk-copied
+  IRA_CUDA(h, cudaMemsetAsync(h->I.p, 0, sizeof(int2) * mp, h->stream));
+  IRA_CUDA(h, cudaMemsetAsync(h->QQ.p, 0, sizeof(double) * 4 * mp, h->stream));
+  if (m > 0) {
+    IRA_CUDA(h, cudaMemcpyAsync(h->I.p, I_pairs, sizeof(int2) * m, cudaMemcpyHostToDevice, h->stream));
+    IRA_CUDA(h, cudaMemcpy2DAsync(h->QQ.p, sizeof(double) * mp, QQ, sizeof(double) * ld_qq, sizeof(double) * m, 4,
+                                  cudaMemcpyHostToDevice, h->stream));
+  }
+  IRA_TRY(upload_Q(h, Q0, ld_q, h->Q0));
+  IRA_TRY(build_csr(h));
+  h->prev_cg = 0;
+  h->uploaded = true;
+  return IRA_OK;
+}
+
+ira_status ira_irls_resident(ira_handle h, int32_t cost, double sigma, int32_t max_iters, double change_th,
+                             int32_t* iters_out, double* runtime_s_out, ira_stats* stats) {
+  if (!h) return IRA_ERR_INVALID_ARG;
+  if (!h->uploaded) return IRA_ERR_NOT_UPLOADED;
+  if (cost < 0 || cost >= kNumCosts) { h->err = "Unknown cost!!"; return IRA_ERR_UNKNOWN_COST; }
+  IRA_CUDA(h, cudaSetDevice(h->device));
+  const auto t0 = std::chrono::steady_clock::now();
+  const int launches0 = h->launches;
+  if (stats) {
+    const double up = stats->t_upload_ms;
+    memset(stats, 0, sizeof *stats);
+    stats->t_upload_ms = up;
+  }
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  IRA_CUDA(h, cudaEventCreate(&ev0));
+  IRA_CUDA(h, cudaEventCreate(&ev1));
+  IRA_CUDA(h, cudaEventRecord(ev0, h->stream));
+
+  const int n = h->n;
+  const int64_t m = h->m;
+  if (n > 0) IRA_CUDA(h, cudaMemcpyAsync(h->Q.p, h->Q0.p, sizeof(double4) * n, cudaMemcpyDeviceToDevice, h->stream));
+  k_fill_f64<<<std::max(1, std::min(cdiv(h->m_pad, 256), h->sms * 8)), 256, 0, h->stream>>>(
+      h->weights.as<double>(), 1.0, h->m_pad);                          // weights.setOnes() (:577)
+  IRA_TRY(launch_check(h, "k_fill_f64"));
+  Ctl init;
+  memset(&init, 0, sizeof init);
+  init.rtol2 = h->opt.cg_rtol * h->opt.cg_rtol;
+  init.cg_max_iters = h->opt.cg_max_iters;
+  *h->h_ctl = init;
+  IRA_CUDA(h, cudaMemcpyAsync(h->ctl.p, h->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, h->stream));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->prev_cg = 0;
+
+  double score = std::numeric_limits<double>::max();                      // :574
+  int iters = 0;
+  ira_status rc = IRA_OK;
+  while (score > change_th && iters < max_iters) {                         // :590
+    IRA_TRY(run_residual(h, h->Q.as<double4>(), 0));                       // :592-593
+    int cg_it = 0, hit = 0;
+    double rel = 0.0;
+    IRA_TRY(solve_pcg(h, &cg_it, &rel, &hit));                             // :596-612
+    if (m > 0) {
+      ProfScope ps(h, KC_WEIGHTS);
+      k_weights<<<std::min(cdiv(m, 256), h->sms * 16), 256, 0, h->stream>>>(
+          h->I.as<int2>(), h->wres.as<double4>(), h->X.as<double4>(), h->weights.as<double>(), m, h->f,
+          cost, sigma);                                                    // :614-727
+      IRA_TRY(launch_check(h, "k_weights"));
+    }
+    {
+      ProfScope ps(h, KC_UPDATE);
+      k_update<<<grid_nodes(h, std::max(1, n - h->f), kRedThreads), kRedThreads, 0, h->stream>>>(
+          h->Q.as<double4>(), h->X.as<double4>(), n, h->f, h->ctl.as<Ctl>(), h->partials.as<double>());  // :729-737
+      IRA_TRY(launch_check(h, "k_update"));
+    }
+    IRA_TRY(fetch_ctl(h));
+    score = h->h_ctl->score;
+    if (stats && iters < IRA_STATS_MAX_ITERS) {
+      stats->score[iters] = score;
+      stats->cg_iters[iters] = cg_it;
+      stats->cg_relres[iters] = rel;
+    }
+    if (stats) { stats->cg_iters_total += cg_it; stats->cg_hit_max += hit; }
+    iters++;                                                               // :739
+    if (!std::isfinite(score)) { if (n - h->f > 0) rc = IRA_ERR_NONFINITE; break; }
+  }
+  IRA_CUDA(h, cudaEventRecord(ev1, h->stream));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev0, ev1);
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  prof_collect(h, stats);
+  if (iters_out) *iters_out = iters;
+  if (runtime_s_out) *runtime_s_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (stats) {
+    stats->irls_iters = iters;
+    stats->t_total_ms = ms;
+    stats->kernel_launches = h->launches - launches0;
+  }
+  if (rc == IRA_ERR_NONFINITE) h->err = "score became non-finite";
+  return rc;
+}
+
+ira_status ira_problem_download(ira_handle h, double* Q, int64_t ld_q, double* weights) {
+  if (!h) return IRA_ERR_INVALID_ARG;
+  if (!h->uploaded) return IRA_ERR_NOT_UPLOADED;
+  IRA_CUDA(h, cudaSetDevice(h->device));
+  const int n = h->n;
+  if (Q && n > 0) {
+    if (ld_q < n) { h->err = "ld_q < n_total"; return IRA_ERR_INVALID_ARG; }
+    k_aos4_to_colmajor<<<grid_nodes(h, n), 256, 0, h->stream>>>(h->Q.as<double4>(), h->stage.as<double>(), n, n, 4);
+    IRA_TRY(launch_check(h, "k_aos4_to_colmajor"));
+    IRA_CUDA(h, cudaMemcpy2DAsync(Q, sizeof(double) * ld_q, h->stage.p, sizeof(double) * n, sizeof(double) * n, 4,
+                                  cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (weights && h->m > 0)
+    IRA_CUDA(h, cudaMemcpyAsync(weights, h->weights.p, sizeof(double) * h->m, cudaMemcpyDeviceToHost, h->stream));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IRA_OK;
+}
+
+ira_status ira_irls(ira_handle h, int64_t m, int64_t n_total, int32_t f, const int32_t* I_pairs, const double* QQ,
+                    int64_t ld_qq, double* Q, int64_t ld_q, int32_t cost, double sigma, int32_t max_iters,
+                    double change_th, double* weights, int32_t* iters_out, double* runtime_s_out,
+                    ira_stats* stats) {
+  const auto t0 = std::chrono::steady_clock::now();
+  IRA_TRY(check_args(h, m, n_total, f, I_pairs, QQ, ld_qq, Q, ld_q));
+  if (m > 0 && !weights) { h->err = "null weights"; return IRA_ERR_INVALID_ARG; }
+  if (cost < 0 || cost >= kNumCosts) { h->err = "Unknown cost!!"; return IRA_ERR_UNKNOWN_COST; }
+  IRA_TRY(ira_problem_upload(h, m, n_total, f, I_pairs, QQ, ld_qq, Q, ld_q));
+  const auto t1 = std::chrono::steady_clock::now();
+  if (stats) stats->t_upload_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  const ira_status rc = ira_irls_resident(h, cost, sigma, max_iters, change_th, iters_out, nullptr, stats);
+  if (rc != IRA_OK && rc != IRA_ERR_NONFINITE) return rc;
+  const auto t2 = std::chrono::steady_clock::now();
+  IRA_TRY(ira_problem_download(h, Q, ld_q, weights));
+  const auto t3 = std::chrono::steady_clock::now();
+  if (stats) stats->t_download_ms = std::chrono::duration<double, std::milli>(t3 - t2).count();
+  if (runtime_s_out) *runtime_s_out = std::chrono::duration<double>(t3 - t0).count();
+  return rc;
+}
+
+// ---- host helpers ---------------------------------------------------------------------------
+ira_status ira_make_A(int64_t m, int32_t n_total, int32_t f, const int32_t* I_pairs, int32_t* col_plus,
+                      int32_t* col_minus) {
+  if (m < 0 || n_total < 0 || f < 0 || (m > 0 && (!I_pairs || !col_plus || !col_minus))) return IRA_ERR_INVALID_ARG;
+  for (int64_t k = 0; k < m; ++k) {
+    const int32_t i = I_pairs[2 * k], j = I_pairs[2 * k + 1];
+    if (i < 0 || j < 0 || i >= n_total || j >= n_total) return IRA_ERR_INVALID_ARG;
+    col_plus[k] = j >= f ? j - f : -1;                       // ral/l1_irls.cpp:770-772
+    col_minus[k] = (j >= f && i >= f) ? i - f : -1;          // :774-776 (skipped when j is fixed)
+  }
+  return IRA_OK;
+}
+
+ira_status ira_quat_normalised(double* Q, int64_t n_total, int64_t ld_q, int32_t f) {
+  if (!Q || ld_q < n_total || f < 0) return IRA_ERR_INVALID_ARG;
+  for (int64_t i = f; i < n_total; ++i) {                    // ral/l1_irls.cpp:985-990
+    double* x = Q + i; double* y = Q + ld_q + i; double* z = Q + 2 * ld_q + i; double* w = Q + 3 * ld_q + i;
+    const double nrm = sqrt(*x * *x + *y * *y + *z * *z + *w * *w);
+    if (nrm > 0.0) { *x /= nrm; *y /= nrm; *z /= nrm; *w /= nrm; }   // Eigen leaves a zero quaternion as is
+  }
+  return IRA_OK;
+}
+
+// ---- probes ---------------------------------------------------------------------------------
+ira_status ira_probe_residual(ira_handle h, double* w_out) {
+  if (!h || !w_out) return IRA_ERR_INVALID_ARG;
+  if (!h->uploaded) return IRA_ERR_NOT_UPLOADED;
+  IRA_CUDA(h, cudaSetDevice(h->device));
+  if (h->m == 0) return IRA_OK;
+  IRA_CUDA(h, cudaMemsetAsync(h->weights.p, 0, sizeof(double) * h->m_pad, h->stream));
+  IRA_TRY(run_residual(h, h->Q0.as<double4>(), 1));
+  k_aos4_to_colmajor<<<std::min(cdiv(h->m, 256), h->sms * 8), 256, 0, h->stream>>>(
+      h->wres.as<double4>(), h->stage.as<double>(), h->m, h->m, 4);
+  IRA_TRY(launch_check(h, "k_aos4_to_colmajor"));
+  IRA_CUDA(h, cudaMemcpyAsync(w_out, h->stage.p, sizeof(double) * 4 * h->m, cudaMemcpyDeviceToHost, h->stream));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IRA_OK;
+}
+
+static ira_status probe_prepare(ira_handle h) {   // weights = 1, residual from Q0, rhs, cg_init: a live CG state
+  k_fill_f64<<<std::max(1, std::min(cdiv(h->m_pad, 256), h->sms * 8)), 256, 0, h->stream>>>(h->weights.as<double>(), 1.0, h->m_pad);
+  IRA_TRY(launch_check(h, "k_fill_f64"));
+  Ctl init;
+  memset(&init, 0, sizeof init);
+  init.rtol2 = 0.0;
+  init.cg_max_iters = 1 << 30;
+  *h->h_ctl = init;
+  IRA_CUDA(h, cudaMemcpyAsync(h->ctl.p, h->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, h->stream));
+  IRA_CUDA(h, cudaMemcpyAsync(h->Q.p, h->Q0.p, sizeof(double4) * h->n, cudaMemcpyDeviceToDevice, h->stream));
+  IRA_TRY(run_residual(h, h->Q.as<double4>(), 0));
+  IRA_TRY(run_rhs(h));
+  IRA_TRY(run_cg_init(h));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IRA_OK;
+}
+
+ira_status ira_probe_laplacian_apply(ira_handle h, const double* weights, const double* X, double* Y) {
+  if (!h || !weights || !X || !Y) return IRA_ERR_INVALID_ARG;
+  if (!h->uploaded) return IRA_ERR_NOT_UPLOADED;
+  IRA_CUDA(h, cudaSetDevice(h->device));
+  const int n = h->n, nf = n - h->f;
+  if (nf <= 0) return IRA_OK;
+  IRA_TRY(probe_prepare(h));
+  if (h->m > 0) {
+    IRA_CUDA(h, cudaMemcpyAsync(h->weights.p, weights, sizeof(double) * h->m, cudaMemcpyHostToDevice, h->stream));
+    k_set_w2<<<std::min(cdiv(h->m, 256), h->sms * 8), 256, 0, h->stream>>>(h->wres.as<double4>(), h->weights.as<double>(), h->m);
+    IRA_TRY(launch_check(h, "k_set_w2"));
+  }
+  IRA_TRY(run_rhs(h));
+  IRA_CUDA(h, cudaMemcpyAsync(h->stage.p, X, sizeof(double) * 3 * nf, cudaMemcpyHostToDevice, h->stream));
+  k_free_to_aos4<<<grid_nodes(h, n), 256, 0, h->stream>>>(h->stage.as<double>(), nf, h->f, h->P.as<double4>(), n);
+  IRA_TRY(launch_check(h, "k_free_to_aos4"));
+  IRA_TRY(run_spmv(h, h->opt.world_size <= 1));
+  k_aos4_to_colmajor<<<grid_nodes(h, nf), 256, 0, h->stream>>>(h->AP.as<double4>() + h->f, h->stage.as<double>(), nf, nf, 3);
+  IRA_TRY(launch_check(h, "k_aos4_to_colmajor"));
+  IRA_CUDA(h, cudaMemcpyAsync(Y, h->stage.p, sizeof(double) * 3 * nf, cudaMemcpyDeviceToHost, h->stream));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IRA_OK;
+}
+
+ira_status ira_probe_time_kernel(ira_handle h, int32_t which, int32_t reps, int32_t flush_l2, double* avg_us_out) {
+  if (!h || !avg_us_out || reps < 1 || which < 0 || which > 5) return IRA_ERR_INVALID_ARG;
+  if (!h->uploaded) return IRA_ERR_NOT_UPLOADED;
+  IRA_CUDA(h, cudaSetDevice(h->device));
+  IRA_TRY(probe_prepare(h));
+  const size_t flush_bytes = 512ull << 20;
+  if (flush_l2) IRA_CUDA(h, h->flush.reserve(flush_bytes));
+  cudaEvent_t a, b;
+  IRA_CUDA(h, cudaEventCreate(&a));
+  IRA_CUDA(h, cudaEventCreate(&b));
+  const int saved_profile = h->opt.profile;
+  h->opt.profile = 0;
+  double total_ms = 0.0;
+  ira_status rc = IRA_OK;
+  auto one = [&]() -> ira_status {
+    switch (which) {
+      case 0: return run_residual(h, h->Q.as<double4>(), 0);
+      case 1: return run_spmv(h, h->opt.world_size <= 1);
+      case 2: return run_rhs(h);
+      case 3:
+        k_weights<<<std::min(cdiv(std::max<int64_t>(h->m, 1), 256), h->sms * 16), 256, 0, h->stream>>>(
+            h->I.as<int2>(), h->wres.as<double4>(), h->X.as<double4>(), h->weights.as<double>(), h->m, h->f,
+            (int)kL1, 0.0872664626);
+        return launch_check(h, "k_weights");
+      case 4:
+        k_update<<<grid_nodes(h, std::max(1, h->n - h->f), kRedThreads), kRedThreads, 0, h->stream>>>(
+            h->Q.as<double4>(), h->X.as<double4>(), h->n, h->f, h->ctl.as<Ctl>(), h->partials.as<double>());
+        return launch_check(h, "k_update");
+      default:
+        k_cg_update<<<grid_nodes(h, h->n, kRedThreads), kRedThreads, 0, h->stream>>>(
+            h->X.as<double4>(), h->R.as<double4>(), h->Z.as<double4>(), h->P.as<double4>(), h->AP.as<double4>(),
+            h->dinv.as<double>(), h->n, h->ctl.as<Ctl>(), h->partials.as<double>());
+        return launch_check(h, "k_cg_update");
+    }
+  };
+  for (int w = 0; w < 3 && rc == IRA_OK; ++w) rc = one();   // warm-up
+  if (rc == IRA_OK) {
+    if (flush_l2) {
+      for (int r = 0; r < reps && rc == IRA_OK; ++r) {
+        cudaMemsetAsync(h->flush.p, r & 0xff, flush_bytes, h->stream);
+        cudaEventRecord(a, h->stream);
+        rc = one();
+        cudaEventRecord(b, h->stream);
+        cudaStreamSynchronize(h->stream);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        total_ms += ms;
+      }
+    } else {
+      cudaEventRecord(a, h->stream);
+      for (int r = 0; r < reps && rc == IRA_OK; ++r) rc = one();
+      cudaEventRecord(b, h->stream);
+      cudaStreamSynchronize(h->stream);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, a, b);
+      total_ms = ms;
+    }
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  h->opt.profile = saved_profile;
+  if (rc != IRA_OK) return rc;
+  IRA_CUDA(h, cudaGetLastError());
+  *avg_us_out = total_ms * 1000.0 / reps;
+  return IRA_OK;
+}
+
+// ---- communicator ---------------------------------------------------------------------------
+ira_status ira_comm_unique_id(uint8_t id_out[128]) {
+  if (!id_out) return IRA_ERR_INVALID_ARG;
+  if (!g_nccl.load()) return IRA_ERR_COMM;
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return IRA_ERR_COMM;
+  memcpy(id_out, &id, 128);
+  return IRA_OK;
+}
+
+ira_status ira_comm_init(ira_handle h, const uint8_t id_in[128]) {
+  if (!h || !id_in) return IRA_ERR_INVALID_ARG;
+  if (h->opt.world_size <= 1) return IRA_OK;
+  if (h->opt.rank < 0 || h->opt.rank >= h->opt.world_size) { h->err = "rank out of range"; return IRA_ERR_INVALID_ARG; }
+  if (!g_nccl.load()) { h->err = "libnccl.so.2 could not be loaded"; return IRA_ERR_COMM; }
+  IRA_CUDA(h, cudaSetDevice(h->device));
+  ncclUniqueId id;
+  memcpy(&id, id_in, 128);
+  ncclResult_t r = g_nccl.CommInitRank(&h->comm, h->opt.world_size, id, h->opt.rank);
+  if (r != ncclSuccess) { h->err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); return IRA_ERR_COMM; }
+  return IRA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,386 @@
+"""CPU oracle for the iRotAvg IRLS rotation-averaging hot path (numpy / scipy, float64).
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product path (irotavg_b200/, include/) may import,
+call, link or execute this file; only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs use it, and only as the checker / reported baseline.
+
+PARITY UNPINNED: the reference ships no expected output, known-answer test or golden vector for
+this path (ral/test.cpp is a CLI, ral/data/ravg_input.txt is input only), and the reference
+cannot be compiled in this image (Eigen, SuiteSparseQR, UMFPACK absent, no network).  The pins
+this oracle is held to instead are (tests/test_oracle.py):
+  1. noise-free known-answer graphs (ground truth recovered to ~1e-15 rad),
+  2. agreement of three independent formulations of the linear step
+     (dense QR least squares on D*A  ==  sparse LU on A^T D^2 A  ==  Jacobi-PCG),
+  3. agreement with the independent plain-C restatement oracle/irls_oracle.c.
+
+Every function cites the reference lines it restates (paths relative to /root/reference).
+The third-party arithmetic is restated from its definition:
+  * SuiteSparseQR<double>(DA, DB)  (ral/l1_irls.cpp:550, system package, version unpinned):
+    X = argmin ||DA X - DB||_F.  Restated as numpy lstsq (dense QR/SVD), sparse LU of the
+    normal equations, or Jacobi-PCG on the normal equations.
+  * Eigen::Quaterniond product (ral/l1_irls.cpp:99-105): the Hamilton product.
+Quaternions are rows [x y z w] (ral/test.cpp:193,221).
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+EPS = 2.2204e-16  # ral/l1_irls.hpp:40
+
+# enum Cost, ral/l1_irls.hpp:56-57 (integer values 0..13 in this order)
+L2, L1, L15, L05, GEMAN_MCCLURE, HUBER, PSEUDO_HUBER, ANDREWS, BISQUARE, CAUCHY, FAIR, \
+    LOGISTIC, TALWAR, WELSCH = range(14)
+COST_NAMES = ["L2", "L1", "L1.5", "L0.5", "Geman-McClure", "Huber", "Pseudo-Huber", "Andrews",
+              "Bisquare", "Cauchy", "Fair", "Logistic", "Talwar", "Welsch"]
+
+
+def parse_cost(name: str) -> int:
+    """ral/test.cpp:35-72 (case-insensitive name -> enum)."""
+    low = name.lower()
+    for k, nm in enumerate(COST_NAMES):
+        if nm.lower() == low:
+            return k
+    raise ValueError("Unknown string. " + name)
+
+
+# --------------------------------------------------------------------------------------------
+# quaternion arithmetic
+# --------------------------------------------------------------------------------------------
+def quat_mult(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Hamilton product a (x) b on rows [x y z w].  ral/l1_irls.cpp:99-105."""
+    ax, ay, az, aw = a[..., 0], a[..., 1], a[..., 2], a[..., 3]
+    bx, by, bz, bw = b[..., 0], b[..., 1], b[..., 2], b[..., 3]
+    out = np.empty(np.broadcast(a, b).shape, dtype=np.float64)
+    out[..., 0] = aw * bx + ax * bw + ay * bz - az * by
+    out[..., 1] = aw * by + ay * bw + az * bx - ax * bz
+    out[..., 2] = aw * bz + az * bw + ax * by - ay * bx
+    out[..., 3] = aw * bw - ax * bx - ay * by - az * bz
+    return out
+
+
+def delta_rel(I: np.ndarray, QQ: np.ndarray, Q: np.ndarray) -> np.ndarray:
+    """resp_k = Q_inv[j] (x) (QQ[k] (x) Q[i]), Q_inv = Q with column w negated.
+    ral/l1_irls.cpp:109-127 (note: -conj(q), not conj(q); the wrap in log_map absorbs it)."""
+    Q_inv = Q.copy()
+    Q_inv[:, 3] *= -1.0
+    return quat_mult(Q_inv[I[:, 1]], quat_mult(QQ, Q[I[:, 0]]))
+
+
+def log_map(w: np.ndarray) -> np.ndarray:
+    """In place: rows -> [axis*theta, theta], theta wrapped to [-pi, pi).  ral/l1_irls.cpp:498-532."""
+    s2 = np.sqrt(w[:, 0] ** 2 + w[:, 1] ** 2 + w[:, 2] ** 2)
+    theta = 2.0 * np.arctan2(s2, w[:, 3])
+    theta = np.where(theta < -np.pi, theta + 2 * np.pi,
+                     np.where(theta >= np.pi, theta - 2 * np.pi, theta))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        aux = theta / s2
+        w[:, 0] *= aux
+        w[:, 1] *= aux
+        w[:, 2] *= aux
+    w[:, 3] = theta
+    w[s2 < EPS, 0:3] = 0.0
+    return w
+
+
+def exp_map(W: np.ndarray) -> np.ndarray:
+    """In place: rows [v, *] -> [v sin(|v|/2)/|v|, cos(|v|/2)], non-finite -> 0.  ral/l1_irls.cpp:471-492."""
+    theta = np.sqrt(W[:, 0] ** 2 + W[:, 1] ** 2 + W[:, 2] ** 2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ang = np.sin(theta / 2.0) / theta
+        W[:, 3] = np.cos(theta / 2.0)
+        W[:, 0] *= ang
+        W[:, 1] *= ang
+        W[:, 2] *= ang
+    W[~np.isfinite(W)] = 0.0
+    return W
+
+
+def quat_normalised(Q: np.ndarray, f: int) -> np.ndarray:
+    """Normalise rows f..n in place.  ral/l1_irls.cpp:982-991."""
+    nrm = np.sqrt((Q[f:] ** 2).sum(axis=1))
+    Q[f:] /= nrm[:, None]
+    return Q
+
+
+def rmat2quat(R: np.ndarray) -> np.ndarray:
+    """3x3 rotation -> [x y z w], exact branch rule of src/ViewGraph.cpp:1175-1203."""
+    q = np.zeros(4)
+    tr = R[0, 0] + R[1, 1] + R[2, 2]
+    if tr > 0.0:
+        s = np.sqrt(tr + 1.0)
+        q[3] = s * 0.5
+        s = 0.5 / s
+        q[0] = (R[2, 1] - R[1, 2]) * s
+        q[1] = (R[0, 2] - R[2, 0]) * s
+        q[2] = (R[1, 0] - R[0, 1]) * s
+    else:
+        i = (2 if R[1, 1] < R[2, 2] else 1) if R[0, 0] < R[1, 1] else (2 if R[0, 0] < R[2, 2] else 0)
+        j = (i + 1) % 3
+        k = (i + 2) % 3
+        s = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0)
+        q[i] = s * 0.5
+        s = 0.5 / s
+        q[3] = (R[k, j] - R[j, k]) * s
+        q[j] = (R[j, i] + R[i, j]) * s
+        q[k] = (R[k, i] + R[i, k]) * s
+    return q
+
+
+def quat2rmat(q: np.ndarray) -> np.ndarray:
+    """Normalised [x y z w] -> 3x3 (Eigen toRotationMatrix; src/ViewGraph.cpp:1426-1433)."""
+    x, y, z, w = q / np.linalg.norm(q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+# --------------------------------------------------------------------------------------------
+# incidence matrix and its mask
+# --------------------------------------------------------------------------------------------
+def edge_mask(I: np.ndarray, f: int):
+    """(has_j, has_i) per edge under make_A's rule: +1 at j-f if j>=f; -1 at i-f only if ALSO
+    i>=f (the `continue` at ral/l1_irls.cpp:771 drops the whole edge when j is fixed)."""
+    has_j = I[:, 1] >= f
+    has_i = has_j & (I[:, 0] >= f)
+    return has_j, has_i
+
+
+def make_A(n: int, f: int, I: np.ndarray):
+    """m x (n-f) sparse incidence matrix.  ral/l1_irls.cpp:755-780.  `n` is the TOTAL node count
+    (ral/test.cpp:288 passes n, src/ViewGraph.cpp:1400 passes num_of_vertices)."""
+    import scipy.sparse as sp
+    m = I.shape[0]
+    has_j, has_i = edge_mask(I, f)
+    rows = np.concatenate([np.nonzero(has_j)[0], np.nonzero(has_i)[0]])
+    cols = np.concatenate([I[has_j, 1] - f, I[has_i, 0] - f])
+    vals = np.concatenate([np.ones(has_j.sum()), -np.ones(has_i.sum())])
+    return sp.csc_matrix((vals, (rows, cols)), shape=(m, n - f))
+
+
+# --------------------------------------------------------------------------------------------
+# robust weights
+# --------------------------------------------------------------------------------------------
+def update_weights(cost: int, sigma: float, E: np.ndarray, weights: np.ndarray) -> np.ndarray:
+    """The cost switch of ral/l1_irls.cpp:617-727.  `weights` are square-root weights (they scale
+    rows of A); returns the new vector (Huber / L2 keep entries of the old one)."""
+    e2 = E[:, 0] ** 2 + E[:, 1] ** 2 + E[:, 2] ** 2  # rowwise().squaredNorm()
+    e = np.sqrt(e2)                                   # rowwise().norm()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if cost == L2:                                                     # :619-620
+            return weights
+        if cost == L05:                                                    # :621-625
+            w = 1.0 / np.power(e2, 3.0 / 8.0)
+            return np.where(w > 1e4, 1e4, w)
+        if cost == L1:                                                     # :626-630
+            w = 1.0 / np.sqrt(e)
+            return np.where(w > 1e4, 1e4, w)
+        if cost == L15:                                                    # :631-635
+            w = 1.0 / np.sqrt(np.sqrt(e))
+            return np.where(w > 1e4, 1e4, w)
+        if cost == GEMAN_MCCLURE:                                          # :636-642
+            return 1.0 / (e2 + sigma * sigma)
+        if cost == HUBER:                                                  # :643-651 (sticky)
+            tun = 1.345 * sigma
+            ee = e / tun
+            w = weights.copy()
+            sel = ee >= 1
+            w[sel] = np.sqrt(1.0 / ee[sel])
+            return w
+        if cost == PSEUDO_HUBER:                                           # :652-658
+            tun = sigma
+            return 1.0 / np.sqrt(np.sqrt(1.0 + e2 / (tun * tun)))
+        if cost == ANDREWS:                                                # :659-677
+            tun = 1.339 * sigma
+            ee = e / tun
+            w = np.sqrt(np.sin(ee) / ee)
+            w = np.where(ee >= np.pi, 0.0, np.where(ee < 1e-4, 1.0, w))
+            # `weights(i) < 0.0001` is false for NaN, so NaN would survive; sin(e)/e<0 only for e>=pi
+            return np.where(w < 1e-4, 1e-4, w)
+        if cost == BISQUARE:                                               # :678-684
+            tun = 4.685 * sigma
+            w = 1.0 - e2 / (tun * tun)
+            return np.where(w < 1e-4, 1e-4, w)
+        if cost == CAUCHY:                                                 # :685-691
+            tun = 2.385 * sigma
+            return 1.0 / np.sqrt(1.0 + e2 / (tun * tun))
+        if cost == FAIR:                                                   # :692-698
+            tun = 1.400 * sigma
+            return 1.0 / np.sqrt(1.0 + e / tun)
+        if cost == LOGISTIC:                                               # :699-707
+            tun = 1.205 * sigma
+            ee = e / tun
+            w = np.sqrt(np.tanh(ee) / ee)
+            return np.where(ee < 1e-4, 1.0, w)
+        if cost == TALWAR:                                                 # :708-714
+            tun = 2.795 * sigma
+            return np.where(e2 < tun * tun, 1.0001, 0.0)
+        if cost == WELSCH:                                                 # :715-722
+            tun = 2.985 * sigma
+            w = np.exp(-0.5 * e2 / (tun * tun))
+            return np.where(w < 1e-4, 1e-4, w)
+    raise ValueError("Unknown cost!!")                                     # :723-726
+
+
+# --------------------------------------------------------------------------------------------
+# linear step: X = argmin || D A X - D w ||_F      (ral/l1_irls.cpp:596-612, ls_solve :536-556)
+# --------------------------------------------------------------------------------------------
+def pcg_jacobi(L, d, B, rtol=1e-13, max_iters=20000):
+    """Jacobi-preconditioned CG on L X = B (3 right-hand sides, independent alpha/beta per column),
+    x0 = 0.  Returns (X, iterations)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dinv = np.where(d > 0, 1.0 / d, 0.0)
+    X = np.zeros_like(B)
+    R = B.copy()
+    Z = R * dinv[:, None]
+    P = Z.copy()
+    rz = (R * Z).sum(axis=0)
+    bn = np.sqrt((B * B).sum(axis=0))
+    it = 0
+    while it < max_iters:
+        rn = np.sqrt((R * R).sum(axis=0))
+        if np.all(rn <= rtol * bn):
+            break
+        AP = L @ P
+        pAp = (P * AP).sum(axis=0)
+        alpha = np.where(pAp > 0, rz / np.where(pAp > 0, pAp, 1.0), 0.0)
+        X += alpha * P
+        R -= alpha * AP
+        Z = R * dinv[:, None]
+        rz_new = (R * Z).sum(axis=0)
+        beta = np.where(rz > 0, rz_new / np.where(rz > 0, rz, 1.0), 0.0)
+        P = Z + beta * P
+        rz = rz_new
+        it += 1
+    return X, it
+
+
+def ls_solve(A, weights: np.ndarray, w3: np.ndarray, solver: str = "direct", pcg_rtol=1e-13):
+    """Restates ls_solve(W3, DA, DB) with DA = diag(weights) A, DB = weights .* w3.
+    solver: 'lstsq' (dense QR/SVD on DA: nearest to SPQR semantics; small graphs only),
+            'direct' (sparse LU of A^T D^2 A), 'pcg' (Jacobi-PCG on A^T D^2 A, x0=0)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    if solver == "lstsq":
+        DA = sp.diags(weights) @ A
+        DB = weights[:, None] * w3
+        X, *_ = np.linalg.lstsq(DA.toarray(), DB, rcond=None)
+        return X, 0
+    w2 = weights * weights
+    At = A.T.tocsr()
+    Lm = (At @ sp.diags(w2) @ A).tocsc()
+    B = At @ (w2[:, None] * w3)
+    if solver == "direct":
+        lu = spla.splu(Lm)
+        X = lu.solve(B)
+        # one step of iterative refinement keeps the normal-equation solve at QR-level accuracy
+        X += lu.solve(B - Lm @ X)
+        return X, 0
+    if solver == "pcg":
+        return pcg_jacobi(Lm.tocsr(), Lm.diagonal(), B, rtol=pcg_rtol)
+    raise ValueError(solver)
+
+
+# --------------------------------------------------------------------------------------------
+# the IRLS loop
+# --------------------------------------------------------------------------------------------
+@dataclass
+class IrlsResult:
+    Q: np.ndarray
+    weights: np.ndarray
+    iters: int
+    runtime: float
+    scores: list = field(default_factory=list)
+    cg_iters: list = field(default_factory=list)
+
+
+def irls(QQ, I, A, cost, sigma, Q, f, max_iters, change_th, solver="direct", pcg_rtol=1e-13,
+         verbose=False) -> IrlsResult:
+    """irotavg::irls, ral/l1_irls.cpp:559-752.  Q is NOT modified; the updated copy is returned.
+    `A` may be None (it is a pure function of (n, f, I), ral/l1_irls.cpp:755-780)."""
+    tic = time.perf_counter()
+    QQ = np.asarray(QQ, dtype=np.float64)
+    I = np.asarray(I, dtype=np.int64).reshape(-1, 2)
+    Q = np.array(Q, dtype=np.float64, copy=True)
+    m = QQ.shape[0]
+    n = Q.shape[0] - f                       # number of variables (:568)
+    if A is None:
+        A = make_A(Q.shape[0], f, I)
+    A = A.tocsr()
+    weights = np.ones(m)                     # :577
+    score = np.finfo(np.float64).max         # :574
+    iters = 0
+    scores, cgs = [], []
+    while score > change_th and iters < max_iters:       # :590
+        w = log_map(delta_rel(I, QQ, Q))                 # :592-593
+        W3, k = ls_solve(A, weights, w[:, :3], solver, pcg_rtol)   # :596-612
+        E = A @ W3 - w[:, :3]                            # :614
+        weights = update_weights(cost, sigma, E, weights)  # :617-727
+        score = float(np.sqrt((W3 * W3).sum(axis=1)).mean())  # :729
+        W = np.zeros((n, 4))
+        W[:, :3] = W3
+        exp_map(W)                                       # :731
+        Q[f:] = quat_mult(Q[f:], W)                      # :734-737 (no renormalisation)
+        iters += 1
+        scores.append(score)
+        cgs.append(k)
+        if verbose:
+            print(f"IRLS iteration: {iters:4d}; Change: {score:10.6g}; solver iters {k}")
+    return IrlsResult(Q=Q, weights=weights, iters=iters, runtime=time.perf_counter() - tic,
+                      scores=scores, cg_iters=cgs)
+
+
+# --------------------------------------------------------------------------------------------
+# spanning-tree initialisation (NEXT row #3 of SURVEY 8(f); needed for the CLI flow / config 1)
+# --------------------------------------------------------------------------------------------
+def init_mst(Q, QQ, I, f):
+    """irotavg::init_mst, ral/l1_irls.cpp:915-979: repeated sweeps over the edge list in order,
+    propagating from flagged to unflagged endpoints.  Order dependent - restated literally."""
+    Q = np.array(Q, dtype=np.float64, copy=True)
+    n = Q.shape[0]
+    m = QQ.shape[0]
+    flags = np.zeros(n, dtype=bool)
+    flags[0] = True
+    count = 1
+    e1s = [int(v) for v in I[:, 0]]
+    e2s = [int(v) for v in I[:, 1]]
+    while count < n:
+        span = False
+        for k in range(m):
+            e1, e2 = e1s[k], e2s[k]
+            if flags[e1] and not flags[e2]:
+                if e2 >= f:
+                    Q[e2] = quat_mult(QQ[k], Q[e1])                       # :941
+                count += 1
+                flags[e2] = True
+                span = True
+            if (not flags[e1]) and flags[e2]:
+                if e1 >= f:
+                    qinv = QQ[k].copy()
+                    qinv[3] *= -1.0                                       # :956-957
+                    Q[e1] = quat_mult(qinv, Q[e2])
+                count += 1
+                flags[e1] = True
+                span = True
+        if not span and count < n:
+            raise RuntimeError("Relative rotations DO NOT SPAN all the nodes in the VIEW GRAPH")
+    return Q
+
+
+# --------------------------------------------------------------------------------------------
+# metrics
+# --------------------------------------------------------------------------------------------
+def geodesic_angles(Qa: np.ndarray, Qb: np.ndarray) -> np.ndarray:
+    """ang(Qa_i^-1 (x) Qb_i) = 2 atan2(|v|, |w|) per row; inputs need not be unit."""
+    Qa = Qa / np.linalg.norm(Qa, axis=1, keepdims=True)
+    Qb = Qb / np.linalg.norm(Qb, axis=1, keepdims=True)
+    conj = Qa * np.array([-1.0, -1.0, -1.0, 1.0])
+    d = quat_mult(conj, Qb)
+    return 2.0 * np.arctan2(np.sqrt((d[:, :3] ** 2).sum(axis=1)), np.abs(d[:, 3]))
+
+
+def geodesic_rms(Qa, Qb, f=0) -> float:
+    a = geodesic_angles(np.asarray(Qa)[f:], np.asarray(Qb)[f:])
+    return float(np.sqrt((a * a).mean())) if a.size else 0.0
