@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py - IRLS iters/sec on the 1M-edge SO(3) graph (BASELINE.json metric, configs[2]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cost L1]
+
+One *step* = one irls() call of 30 IRLS iterations (max_iters = 30, change_th = -1 so that all 30
+run; ral/l1_irls.cpp:590) on the synthetic random SO(3) graph n = 100 000 / m = 1 000 000
+(seed 20190319).
+  value      IRLS iterations / second, graph already resident in HBM (ira_irls_resident), device
+             time from CUDA events recorded on the library's launch stream, max over ranks.
+  e2e        the same metric through the host-buffer C-ABI call ira_irls(): pinned host buffers in,
+             H2D of (I, QQ, Q), CSR build, 30 iterations, D2H of (Q, weights) inside the timed region.
+  roofline   the dominant kernel (SpMV of the PCG solve): algorithmic bytes 16 m + 48 n per launch
+             over its mean launch duration measured with CUDA events around every SpMV launch of
+             a profiled step, against MEASURED_PEAKS.json's HBM copy bandwidth.
+  cpu_baseline  the oracle port (numpy/scipy restatement or, when built, the C restatement) timed
+             on the host cores on a bounded sample of the same call.
+N > 1 (launched by torchrun, one rank per GPU): the SAME graph with its edges sharded over the
+ranks (strong scaling), node vectors all-reduced with NCCL once per PCG iteration.
+`--impl reference` times the CPU port alone (the reference itself cannot be built here: no Eigen /
+SuiteSparse in the image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_NODES = 100_000
+M_EDGES = 1_000_000
+IRLS_ITERS = 30
+SIGMA = 5 * np.pi / 180.0
+COSTS = {"L2": 0, "L1": 1, "L1.5": 2, "L0.5": 3, "Geman-McClure": 4, "Huber": 5}
+METRIC = "IRLS iters/sec on 1M-edge SO(3) graph"
+UNIT = "irls_iters/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_graph():
+    from oracle import graphs as G
+    return G.random_graph(n=N_NODES, m=M_EDGES)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_port_run(g, cost, iters):
+    """Returns (irls_iters_per_s, kind, cores, sample_text, extra)."""
+    from oracle import irls_oracle as O
+    try:
+        from oracle import cport
+        have_c = cport.available()
+    except Exception:
+        have_c = False
+    if have_c:
+        threads = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        r = cport.irls(g.QQ, g.I, cost, SIGMA, g.Q0, g.f, iters, -1.0, cg_rtol=1e-10, threads=threads)
+        dt = time.perf_counter() - t0
+        return iters / dt, "port", threads, (f"first {iters} of the 30 IRLS iterations of the same call, C restatement "
+                                             f"(oracle/irls_oracle.c, OpenMP {threads} threads, Jacobi-PCG rtol 1e-10; "
+                                             "the reference's SuiteSparseQR solve cannot run this graph: ~40 GB fill)"), \
+            {"cg_iters": list(r["cg_iters"])}
+    t0 = time.perf_counter()
+    r = O.irls(g.QQ, g.I, None, cost, SIGMA, g.Q0, g.f, iters, -1.0, solver="pcg", pcg_rtol=1e-10)
+    dt = time.perf_counter() - t0
+    return iters / dt, "port", 1, (f"first {iters} of the 30 IRLS iterations of the same call, numpy/scipy restatement "
+                                   "(oracle/irls_oracle.py, 1 thread, Jacobi-PCG rtol 1e-10)"), {"cg_iters": r.cg_iters}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    g = make_graph()
+    cost = COSTS[args.cost]
+    sample_iters = args.ref_iters
+    for _ in range(min(args.warmup, 1)):
+        cpu_port_run(g, cost, 1)
+    vals = []
+    extra = {}
+    kind, cores, sample = "port", 1, ""
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        v, kind, cores, sample, extra = cpu_port_run(g, cost, sample_iters)
+        vals.append(v)
+    dt = time.perf_counter() - t_all
+    value = sample_iters * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, **extra},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"configs[2]: synthetic random SO(3) graph n={N_NODES} m={M_EDGES} (path + uniform pairs, "
+                    f"sigma_n=0.05 rad, 10% outliers, seed 20190319), {IRLS_ITERS} IRLS iters per step, cost {args.cost}, "
+                    "sigma 5 deg, f=1",
+        "cost": args.cost, "irls_iters_per_step": IRLS_ITERS, "cg_rtol": 1e-10,
+        "parallelism": "single GPU" if world == 1 else f"edges sharded over {world} ranks, NCCL all-reduce of node vectors",
+        "l2": "512 MB memset between timed steps flushes L2 (working set ~150 MB also exceeds the 126 MB L2)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import irotavg_b200 as ira
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the library has no CPU path (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    g = make_graph()
+    cost = COSTS[args.cost]
+    m, n, f = g.m, g.n, g.f
+    lo, hi = (m * rank) // world, (m * (rank + 1)) // world          # this rank's edge shard
+    I_loc = np.ascontiguousarray(g.I[lo:hi])
+    QQ_loc = np.asfortranarray(g.QQ[lo:hi])
+    m_loc = hi - lo
+
+    s = ira.Solver(device=local_rank, world_size=world, rank=rank)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(ira.Solver.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        s.comm_init(bytes(uid.cpu().numpy().tobytes()))
+    ext = torch.cuda.ExternalStream(s.stream_ptr, device=torch.device("cuda", local_rank))
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident arm (value) -----------------------------------------------------------------
+    s.upload(QQ_loc, I_loc, g.Q0, f)
+
+    def resident_step():
+        with torch.cuda.stream(ext):
+            flush.zero_()                                    # L2 flush, outside the event pair
+            a = torch.cuda.Event(enable_timing=True)
+            b = torch.cuda.Event(enable_timing=True)
+            a.record(ext)
+            info = s.irls_resident(cost, SIGMA, IRLS_ITERS, -1.0)
+            b.record(ext)
+        b.synchronize()
+        return a.elapsed_time(b), info
+
+    for _ in range(args.warmup):
+        resident_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_wall0 = time.perf_counter()
+    dev_ms, launches, infos = 0.0, 0, []
+    for _ in range(args.steps):
+        ms, info = resident_step()
+        dev_ms += ms
+        launches += info.kernel_launches
+        infos.append(info)
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1000.0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = max_over_ranks(dev_ms)
+    value = IRLS_ITERS * args.steps / (dev_ms / 1000.0)
+    Q_res, w_res = s.download()
+
+    # ---- e2e arm: host-buffer C-ABI call, pinned buffers --------------------------------------
+    def pinned(a, order):
+        t = torch.empty(a.size, dtype=torch.float64 if a.dtype == np.float64 else torch.int32).pin_memory()
+        v = t.numpy().reshape(a.shape, order=order)
+        v[...] = a
+        return t, v
+    keep = []
+    tI, pI = pinned(I_loc, "C"); keep.append(tI)
+    tQQ, pQQ = pinned(QQ_loc, "F"); keep.append(tQQ)
+    tQ, pQ = pinned(np.asfortranarray(g.Q0), "F"); keep.append(tQ)
+    tW, pW = pinned(np.zeros(m_loc), "C"); keep.append(tW)
+    Q0f = np.asfortranarray(g.Q0)
+
+    def e2e_step():
+        pQ[...] = Q0f                                       # host-side reset of the in/out buffer (untimed)
+        with torch.cuda.stream(ext):
+            flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        info = s.irls_inplace(pQQ, pI, pQ, pW, cost, SIGMA, f, IRLS_ITERS, -1.0)
+        return (time.perf_counter() - t0) * 1000.0, info
+
+    e2e_ms = 0.0
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        ms, info_e = e2e_step()
+        e2e_ms += ms
+    barrier()
+    e2e_ms = max_over_ranks(e2e_ms)
+    e2e_value = IRLS_ITERS * e2e_steps / (e2e_ms / 1000.0)
+    h2d = I_loc.nbytes + QQ_loc.nbytes + Q0f.nbytes
+    d2h = Q0f.nbytes + 8 * m_loc
+    same = bool(np.array_equal(np.ascontiguousarray(pQ), Q_res))
+
+    # ---- roofline of the dominant kernel, measured live ----------------------------------------
+    peak, peak_src = measured_peak()
+    roof = None
+    prof_share = None
+    if world == 1:
+        sp = ira.Solver(device=local_rank, profile=True)
+        sp.upload(QQ_loc, I_loc, g.Q0, f)
+        sp.irls_resident(cost, SIGMA, 3, -1.0)
+        pinfo = sp.irls_resident(cost, SIGMA, IRLS_ITERS, -1.0)
+        pr = pinfo.profile
+        spmv_us = 1000.0 * pr["spmv"]["ms"] / pr["spmv"]["launches"]
+        res_us = 1000.0 * pr["residual"]["ms"] / pr["residual"]["launches"]
+        tot = sum(v["ms"] for v in pr.values())
+        prof_share = {k: round(v["ms"] / tot, 4) for k, v in pr.items()}
+        spmv_bytes = 16 * m + 48 * n
+        res_bytes = 72 * m + 56 * n
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as fh:
+                traffic = json.load(fh)
+        ach = spmv_bytes / (spmv_us * 1e-6) / 1e9
+        roof = {
+            "kernel": "k_spmv (A^T D^2 A p, 3 RHS) inside the PCG loop", "bound": "hbm", "achieved": ach, "peak": peak,
+            "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+            "traffic": (traffic or {}).get("k_spmv"), "algorithmic_bytes_per_launch": spmv_bytes,
+            "launch_us": spmv_us, "launches_timed": pr["spmv"]["launches"],
+            "note": "launch duration = CUDA events around every SpMV launch of a profiled 30-iteration step on the "
+                    "launch stream; the ~30 MB SpMV working set is L2-resident between PCG iterations",
+            "cold_l2_us": sp.time_kernel(1, 20, True),
+            "share_of_step": prof_share.get("spmv"),
+            "residual_kernel": {"launch_us": res_us, "algorithmic_bytes_per_launch": res_bytes,
+                                "achieved": res_bytes / (res_us * 1e-6) / 1e9,
+                                "frac": res_bytes / (res_us * 1e-6) / 1e9 / peak,
+                                "cold_l2_us": sp.time_kernel(0, 20, True),
+                                "traffic": (traffic or {}).get("k_residual")},
+        }
+        sp.close()
+
+    # ---- parity against the oracle on the run itself (bounded: the first 2 iterations) ----------
+    cpu = None
+    rms = None
+    if rank == 0 and world == 1:
+        from oracle import irls_oracle as O
+        v, kind, cores, sample, extra = cpu_port_run(g, cost, args.ref_iters)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+        ref = O.irls(g.QQ, g.I, None, cost, SIGMA, g.Q0, f, 2, -1.0, solver="pcg", pcg_rtol=1e-13)
+        s2 = ira.Solver(device=local_rank)
+        Q2, _, _ = s2.irls(g.QQ, g.I, None, cost, SIGMA, g.Q0, f, 2, -1.0)
+        s2.close()
+        rms = O.geodesic_rms(Q2, ref.Q, f)
+
+    if rank == 0:
+        info = infos[-1]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "upload_ms": info_e.upload_ms, "download_ms": info_e.download_ms,
+                    "bitwise_equal_to_resident": same},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "wall_ms_per_step": wall_ms / args.steps,
+            "cg_iters_per_step": int(sum(info.cg_iters)), "cg_hit_max": int(info.cg_hit_max),
+            "final_score": info.scores[-1] if info.scores else None,
+            "geodesic_rms_vs_oracle_2iters_rad": rms,
+        }
+        if roof is not None:
+            line["roofline"] = roof
+            line["kernel_time_share"] = prof_share
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    s.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cost", default="L1", choices=sorted(COSTS))
+    ap.add_argument("--ref-iters", type=int, default=3, help="IRLS iterations in the CPU port's bounded sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -88,6 +88,9 @@ const char* ira_status_string(ira_status s);
 const char* ira_last_error(ira_handle h);      /* text of the last failure on this handle          */
 int32_t     ira_abi_version(void);
 int32_t     ira_device_count(void);            /* usable CUDA devices (0 on a CPU-only box)        */
+/* The CUDA stream (cudaStream_t) every kernel of this handle is launched on, so that a harness
+ * can record its own CUDA events on it. */
+ira_status  ira_get_stream(ira_handle h, void** stream_out);
 
 /* ---- irotavg::irls  (ral/l1_irls.hpp:103-106, ral/l1_irls.cpp:559-752) ----------------------
  * Host buffers in, host buffers out.  Q rows [f, n_total) are updated in place, `weights` (m)

@@ -17,7 +17,7 @@ STATS_MAX_ITERS = 256
 # every symbol include/ira.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
     "ira_options_default", "ira_create", "ira_destroy", "ira_status_string", "ira_last_error",
-    "ira_abi_version", "ira_device_count", "ira_irls", "ira_problem_upload", "ira_irls_resident",
+    "ira_abi_version", "ira_device_count", "ira_get_stream", "ira_irls", "ira_problem_upload", "ira_irls_resident",
     "ira_problem_download", "ira_make_A", "ira_quat_normalised", "ira_probe_residual",
     "ira_probe_laplacian_apply", "ira_probe_time_kernel", "ira_comm_unique_id", "ira_comm_init",
 ]
@@ -89,6 +89,7 @@ def load():
         "ira_last_error": (C.c_char_p, [H]),
         "ira_abi_version": (i32, []),
         "ira_device_count": (i32, []),
+        "ira_get_stream": (i32, [H, C.POINTER(C.c_void_p)]),
         "ira_irls": (i32, [H, i64, i64, i32, pi32, pf64, i64, pf64, i64, i32, f64, i32, f64, pf64,
                            pi32, pf64, C.POINTER(Stats)]),
         "ira_problem_upload": (i32, [H, i64, i64, i32, pi32, pf64, i64, pf64, i64]),

@@ -125,7 +125,31 @@ class Solver:
     def __exit__(self, *a):
         self.close()
 
+    @property
+    def stream_ptr(self) -> int:
+        """cudaStream_t of this handle as an integer (for torch.cuda.ExternalStream)."""
+        p = C.c_void_p()
+        self._check(self._lib.ira_get_stream(self._h, C.byref(p)), self._h)
+        return p.value or 0
+
     # -- irotavg::irls ------------------------------------------------------------------------
+    def irls_inplace(self, QQ_f, I_pairs, Q_f, weights, cost, sigma, f, max_iters, change_th) -> IrlsInfo:
+        """ira_irls on caller-owned buffers without any copy: QQ_f (m x 4) and Q_f (n x 4) must be
+        F-ordered float64, I_pairs C-ordered int32 (m x 2), weights float64 (m).  Q_f and weights
+        are overwritten - exactly the in/out contract of the reference signature."""
+        assert QQ_f.flags.f_contiguous and Q_f.flags.f_contiguous and I_pairs.flags.c_contiguous
+        assert QQ_f.dtype == np.float64 and Q_f.dtype == np.float64 and I_pairs.dtype == np.int32
+        assert weights.dtype == np.float64 and weights.flags.c_contiguous
+        m, n = QQ_f.shape[0], Q_f.shape[0]
+        iters = C.c_int32(0)
+        runtime = C.c_double(0.0)
+        st = Stats()
+        self._check(self._lib.ira_irls(self._h, m, n, int(f), _pi(I_pairs), _pd(QQ_f), max(m, 1), _pd(Q_f),
+                                       max(n, 1), int(cost), float(sigma), int(max_iters),
+                                       float(change_th), _pd(weights), C.byref(iters), C.byref(runtime),
+                                       C.byref(st)), self._h)
+        return _info(st, iters.value, runtime.value)
+
     def irls(self, QQ, I, A, cost, sigma, Q, f, max_iters, change_th):
         """irotavg::irls (ral/l1_irls.hpp:103-106).  `A` is accepted for signature parity and
         ignored (pure function of (n, f, I)).  Returns (Q_new, weights, info); Q is not modified."""

@@ -94,6 +94,8 @@ struct ira_context {
   std::vector<Span> spans;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
+  double prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int prof_c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int launches = 0;
   int prev_cg = 0;
 };
@@ -129,10 +131,23 @@ cudaEvent_t prof_event(ira_context* h) {
   }
   return h->ev_pool[h->ev_used++];
 }
+// Resolve the recorded event pairs into the per-class accumulators (synchronises the stream).
+void prof_flush(ira_context* h) {
+  if (h->spans.empty()) return;
+  cudaStreamSynchronize(h->stream);
+  for (auto& s : h->spans) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s.a, s.b);
+    h->prof_t[s.cls] += ms; h->prof_c[s.cls] += 1;
+  }
+  h->spans.clear();
+  h->ev_used = 0;
+}
 struct ProfScope {
   ira_context* h; int idx = -1;
   ProfScope(ira_context* h_, int cls) : h(h_) {
     if (h->opt.profile) {
+      if (h->spans.size() >= 8192) prof_flush(h);
       ira_context::Span s{cls, prof_event(h), prof_event(h)};
       cudaEventRecord(s.a, h->stream);
       h->spans.push_back(s);
@@ -144,15 +159,9 @@ struct ProfScope {
 
 void prof_collect(ira_context* h, ira_stats* st) {
   if (!h->opt.profile) return;
-  cudaStreamSynchronize(h->stream);
-  double t[KC_N] = {0}; int c[KC_N] = {0};
-  for (auto& s : h->spans) {
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, s.a, s.b);
-    t[s.cls] += ms; c[s.cls] += 1;
-  }
-  h->spans.clear();
-  h->ev_used = 0;
+  prof_flush(h);
+  double t[KC_N]; int c[KC_N];
+  for (int k = 0; k < KC_N; ++k) { t[k] = h->prof_t[k]; c[k] = h->prof_c[k]; h->prof_t[k] = 0.0; h->prof_c[k] = 0; }
   if (st) {
     st->t_residual_ms = t[KC_RESIDUAL]; st->n_residual = c[KC_RESIDUAL];
     st->t_rhs_ms = t[KC_RHS]; st->n_rhs = c[KC_RHS];
@@ -441,6 +450,12 @@ const char* ira_status_string(ira_status s) {
     case IRA_ERR_NOT_SPANNING: return "Relative rotations DO NOT SPAN all the nodes in the VIEW GRAPH";
   }
   return "unknown status";
+}
+
+ira_status ira_get_stream(ira_handle h, void** stream_out) {
+  if (!h || !stream_out) return IRA_ERR_INVALID_ARG;
+  *stream_out = (void*)h->stream;
+  return IRA_OK;
 }
 
 const char* ira_last_error(ira_handle h) { return h ? h->err.c_str() : "null handle"; }

@@ -154,7 +154,7 @@ def test_config3_full_size(solver):
     assert np.all(np.diff(s[2:]) < 0)
     assert np.abs(np.linalg.norm(Q, axis=1) - 1).max() < 1e-12
     assert np.array_equal(Q[0], g.Q0[0])
-    assert O.geodesic_rms(Q, g.Qgt, g.f) < 0.25 * O.geodesic_rms(g.Q0, g.Qgt, g.f)
+    assert O.geodesic_rms(Q, g.Qgt, g.f) < 0.5 * O.geodesic_rms(g.Q0, g.Qgt, g.f)
     # determinism: the same call twice is bitwise identical (atomic-free reductions)
     Q2, w2, _ = solver.irls(g.QQ, g.I, None, O.GEMAN_MCCLURE, SIGMA, g.Q0, g.f, 30, -1.0)
     assert np.array_equal(Q, Q2) and np.array_equal(w, w2)
