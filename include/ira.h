@@ -57,11 +57,13 @@ typedef struct ira_options {
   int32_t cg_max_iters;    /* hard cap per linear solve                                           */
   double  cg_rtol;         /* stop when ||r_c|| <= cg_rtol * ||b_c|| for each of the 3 columns    */
   int32_t cg_check_every;  /* host polls the device-side convergence flag every this many iters   */
-  int32_t lanes_per_row;   /* SpMV sub-warp width: 0 = auto from the mean degree, else 2..32      */
+  int32_t lanes_per_row;   /* 0 = SELL-32 thread-per-row kernels (default); 2..32 = CSR kernels
+                              with that many lanes per row (forces solver 1)                       */
   int32_t world_size;      /* >1: edges are sharded over ranks, node vectors all-reduced (NCCL)   */
   int32_t rank;
   int32_t profile;         /* 1: record CUDA-event timings per kernel class into ira_stats        */
-  int32_t solver;          /* PCG driver: 0 = auto, 1 = one kernel per step, host-polled convergence */
+  int32_t solver;          /* PCG driver: 0 = auto (persistent cooperative kernel on one GPU), 1 = one
+                              kernel per CG step with host-polled convergence, 2 = persistent       */
   int32_t reserved[6];
 } ira_options;
 
@@ -79,6 +81,11 @@ typedef struct ira_stats {
   /* profile=1 only: summed device time and launch count per kernel class                        */
   double  t_residual_ms, t_rhs_ms, t_spmv_ms, t_cgvec_ms, t_weights_ms, t_update_ms, t_comm_ms;
   int32_t n_residual, n_rhs, n_spmv, n_cgvec, n_weights, n_update, n_comm;
+  /* persistent solve (one cooperative kernel per linear step): event time of those kernels
+   * (profile=1), and - always - block 0's in-kernel clocks: time in the SpMV+reduction phases, in
+   * the vector-update phases, whole-kernel time, number of SpMV phases executed                   */
+  int32_t n_pcg, pcg_spmv_phases;
+  double  t_pcg_ms, pcg_spmv_ms, pcg_update_ms, pcg_kernel_ms;
 } ira_stats;
 
 ira_status  ira_options_default(ira_options* opt);

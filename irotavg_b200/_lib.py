@@ -56,6 +56,9 @@ class Stats(C.Structure):
         ("n_residual", C.c_int32), ("n_rhs", C.c_int32), ("n_spmv", C.c_int32),
         ("n_cgvec", C.c_int32), ("n_weights", C.c_int32), ("n_update", C.c_int32),
         ("n_comm", C.c_int32),
+        ("n_pcg", C.c_int32), ("pcg_spmv_phases", C.c_int32),
+        ("t_pcg_ms", C.c_double), ("pcg_spmv_ms", C.c_double), ("pcg_update_ms", C.c_double),
+        ("pcg_kernel_ms", C.c_double),
     ]
 
 

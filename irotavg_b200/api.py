@@ -60,7 +60,11 @@ class IrlsInfo:
 def _info(st: Stats, iters: int, runtime: float) -> IrlsInfo:
     k = min(st.irls_iters, _lib.STATS_MAX_ITERS)
     prof = {}
-    for name in ("residual", "rhs", "spmv", "cgvec", "weights", "update", "comm"):
+    if st.pcg_spmv_phases:
+        prof["pcg_phases"] = {"spmv_ms": st.pcg_spmv_ms, "update_ms": st.pcg_update_ms,
+                              "kernel_ms": st.pcg_kernel_ms, "spmv_phases": st.pcg_spmv_phases,
+                              "spmv_us_per_phase": 1000.0 * st.pcg_spmv_ms / st.pcg_spmv_phases}
+    for name in ("residual", "rhs", "spmv", "cgvec", "weights", "update", "comm", "pcg"):
         cnt = getattr(st, "n_" + name)
         if cnt:
             prof[name] = {"ms": getattr(st, "t_" + name + "_ms"), "launches": cnt}

@@ -18,7 +18,10 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_scan.cuh>
+
 #include "ira_kernels.cuh"
+#include "ira_pcg.cuh"
 
 using namespace ira;
 
@@ -41,7 +44,7 @@ struct DevBuf {
   template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
-enum KClass { KC_RESIDUAL = 0, KC_RHS, KC_SPMV, KC_CGVEC, KC_WEIGHTS, KC_UPDATE, KC_COMM, KC_OTHER, KC_N };
+enum KClass { KC_RESIDUAL = 0, KC_RHS, KC_SPMV, KC_CGVEC, KC_WEIGHTS, KC_UPDATE, KC_COMM, KC_PCG, KC_N };
 
 // NCCL resolved at run time so that the single-GPU library has no link-time dependency on it.
 struct NcclApi {
@@ -82,7 +85,14 @@ struct ira_context {
 
   DevBuf I, QQ, weights, wres, Q, Q0, stage;
   DevBuf rowptr, ent_col, ent_eid, ent_w2, keys, vals, cubtmp;
-  DevBuf X, R, Z, P, AP, B, diag, dinv;
+  DevBuf X, R, Z, P, AP, B, diag, dinv, S;
+  // SELL-32-sigma copy of the pattern (ira_pcg.cuh)
+  DevBuf sell_row, slice_off, slice_width, slice_cnt, sell_col, sell_eid, sell_w2;
+  int nslices = 0, npos = 0;
+  int64_t sell_total = 0;
+  bool fmt_csr = false;      // multi-kernel path on the CSR sub-warp kernels (lanes_per_row set)
+  bool persistent = true;    // one cooperative kernel per linear solve
+  int pcg_blocks_per_sm = 0;
   DevBuf ctl, partials, bad, flush;
   Ctl* h_ctl = nullptr;  // pinned
 
@@ -170,6 +180,7 @@ void prof_collect(ira_context* h, ira_stats* st) {
     st->t_weights_ms = t[KC_WEIGHTS]; st->n_weights = c[KC_WEIGHTS];
     st->t_update_ms = t[KC_UPDATE]; st->n_update = c[KC_UPDATE];
     st->t_comm_ms = t[KC_COMM]; st->n_comm = c[KC_COMM];
+    st->t_pcg_ms = t[KC_PCG]; st->n_pcg = c[KC_PCG];
   }
 }
 
@@ -219,8 +230,19 @@ ira_status run_rhs_t(ira_context* h) {
       h->B.as<double4>(), h->diag.as<double>(), h->n);
   return launch_check(h, "k_rhs_diag");
 }
+int grid_slices(const ira_context* h) {
+  return std::max(1, std::min(cdiv((int64_t)h->nslices * 32, 256), h->sms * 8));
+}
+
 ira_status run_rhs(ira_context* h) {
   ProfScope ps(h, KC_RHS);
+  if (!h->fmt_csr) {
+    k_sell_rhs<<<grid_slices(h), 256, 0, h->stream>>>(h->sell_row.as<int>(), h->slice_off.as<int>(),
+                                                      h->slice_width.as<int>(), h->sell_eid.as<int>(),
+                                                      h->wres.as<double4>(), h->sell_w2.as<double>(),
+                                                      h->B.as<double4>(), h->diag.as<double>(), h->nslices);
+    return launch_check(h, "k_sell_rhs");
+  }
   switch (h->lpr) {
     case 2: return run_rhs_t<2>(h);
     case 4: return run_rhs_t<4>(h);
@@ -247,6 +269,19 @@ ira_status run_spmv_t(ira_context* h, bool fuse) {
 }
 ira_status run_spmv(ira_context* h, bool fuse) {
   ProfScope ps(h, KC_SPMV);
+  if (!h->fmt_csr) {
+    if (fuse)
+      k_spmv_sell<true><<<grid_slices(h), 256, 0, h->stream>>>(
+          h->sell_row.as<int>(), h->slice_off.as<int>(), h->slice_width.as<int>(), h->sell_col.as<int>(),
+          h->sell_w2.as<double>(), h->P.as<double4>(), h->AP.as<double4>(), h->nslices, h->ctl.as<Ctl>(),
+          h->partials.as<double>());
+    else
+      k_spmv_sell<false><<<grid_slices(h), 256, 0, h->stream>>>(
+          h->sell_row.as<int>(), h->slice_off.as<int>(), h->slice_width.as<int>(), h->sell_col.as<int>(),
+          h->sell_w2.as<double>(), h->P.as<double4>(), h->AP.as<double4>(), h->nslices, h->ctl.as<Ctl>(),
+          h->partials.as<double>());
+    return launch_check(h, "k_spmv_sell");
+  }
   switch (h->lpr) {
     case 2: return run_spmv_t<2>(h, fuse);
     case 4: return run_spmv_t<4>(h, fuse);
@@ -306,6 +341,29 @@ ira_status fetch_ctl(ira_context* h) {
   return IRA_OK;
 }
 
+// One linear step as ONE cooperative kernel (ira_pcg.cuh); nothing is read back here - the
+// iteration count and residual norms stay in the device control block until the IRLS iteration's
+// single host synchronisation.
+ira_status solve_pcg_persistent(ira_context* h) {
+  IRA_TRY(run_rhs(h));
+  PcgParams pp;
+  pp.n = h->n; pp.nslices = h->nslices; pp.max_iters = std::max(0, h->opt.cg_max_iters);
+  pp.rtol2 = h->opt.cg_rtol * h->opt.cg_rtol;
+  pp.sell_row = h->sell_row.as<int>(); pp.slice_off = h->slice_off.as<int>(); pp.slice_width = h->slice_width.as<int>();
+  pp.sell_col = h->sell_col.as<int>(); pp.sell_w2 = h->sell_w2.as<double>();
+  pp.B = h->B.as<double4>(); pp.diag = h->diag.as<double>();
+  pp.X = h->X.as<double4>(); pp.R = h->R.as<double4>(); pp.U = h->Z.as<double4>(); pp.W = h->AP.as<double4>();
+  pp.P = h->P.as<double4>(); pp.S = h->S.as<double4>();
+  pp.dinv = h->dinv.as<double>(); pp.partials = h->partials.as<double>(); pp.ctl = h->ctl.as<Ctl>();
+  const int warps_per_block = kPcgThreads / 32;
+  const int grid = std::max(1, std::min(cdiv(h->nslices, warps_per_block), h->sms * h->pcg_blocks_per_sm));
+  void* args[] = {(void*)&pp};
+  ProfScope ps(h, KC_PCG);
+  IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_pcg_persistent, dim3(grid), dim3(kPcgThreads), args, 0, h->stream));
+  h->launches++;
+  return IRA_OK;
+}
+
 // One linear step: Jacobi-PCG on A^T D^2 A X = A^T D^2 w, x0 = 0 (replaces ls_solve, :536-556).
 ira_status solve_pcg(ira_context* h, int* iters_out, double* relres_out, int* hit_max) {
   IRA_TRY(run_rhs(h));
@@ -356,7 +414,7 @@ ira_status alloc_problem(ira_context* h, int64_t m, int n) {
   IRA_CUDA(h, h->ent_w2.reserve(sizeof(double) * (size_t)std::max<int64_t>(2 * m, 1)));
   IRA_CUDA(h, h->keys.reserve(sizeof(int) * (size_t)std::max<int64_t>(4 * m, 1)));
   IRA_CUDA(h, h->vals.reserve(sizeof(int) * (size_t)std::max<int64_t>(4 * m, 1)));
-  for (DevBuf* b : {&h->X, &h->R, &h->Z, &h->P, &h->AP, &h->B})
+  for (DevBuf* b : {&h->X, &h->R, &h->Z, &h->P, &h->AP, &h->B, &h->S})
     IRA_CUDA(h, b->reserve(sizeof(double4) * (size_t)std::max(n, 1)));
   IRA_CUDA(h, h->diag.reserve(sizeof(double) * (size_t)std::max(n, 1)));
   IRA_CUDA(h, h->dinv.reserve(sizeof(double) * (size_t)std::max(n, 1)));
@@ -397,6 +455,42 @@ ira_status build_csr(ira_context* h) {
   h->nnz = host[0];
   h->lpr = pick_lpr(h);
   return IRA_OK;
+}
+
+// SELL-32-sigma copy of the CSR pattern (ira_pcg.cuh): window sort by degree, slice offsets, fill.
+ira_status build_sell(ira_context* h) {
+  const int n = h->n;
+  const int nwin = std::max(1, cdiv(n, kSellSigma));
+  h->npos = nwin * kSellSigma;
+  h->nslices = h->npos / kSellC;
+  IRA_CUDA(h, h->sell_row.reserve(sizeof(int) * (size_t)h->npos));
+  IRA_CUDA(h, h->slice_width.reserve(sizeof(int) * ((size_t)h->nslices + 1)));
+  IRA_CUDA(h, h->slice_cnt.reserve(sizeof(int) * ((size_t)h->nslices + 1)));
+  IRA_CUDA(h, h->slice_off.reserve(sizeof(int) * ((size_t)h->nslices + 1)));
+  IRA_CUDA(h, cudaMemsetAsync(h->slice_cnt.p, 0, sizeof(int) * ((size_t)h->nslices + 1), h->stream));
+  k_sell_sort<<<nwin, kSellSigma, 0, h->stream>>>(h->rowptr.as<int>(), n, h->sell_row.as<int>(),
+                                                 h->slice_width.as<int>(), h->slice_cnt.as<int>());
+  IRA_TRY(launch_check(h, "k_sell_sort"));
+  size_t tmp_bytes = 0;
+  IRA_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->slice_cnt.as<int>(), h->slice_off.as<int>(),
+                                            h->nslices + 1, h->stream));
+  IRA_CUDA(h, h->cubtmp.reserve(tmp_bytes));
+  IRA_CUDA(h, cub::DeviceScan::ExclusiveSum(h->cubtmp.p, tmp_bytes, h->slice_cnt.as<int>(), h->slice_off.as<int>(),
+                                            h->nslices + 1, h->stream));
+  h->launches += 2;
+  int total = 0;
+  IRA_CUDA(h, cudaMemcpyAsync(&total, h->slice_off.as<int>() + h->nslices, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->sell_total = total;
+  const size_t cap = (size_t)std::max(total, 1);
+  IRA_CUDA(h, h->sell_col.reserve(sizeof(int) * cap));
+  IRA_CUDA(h, h->sell_eid.reserve(sizeof(int) * cap));
+  IRA_CUDA(h, h->sell_w2.reserve(sizeof(double) * cap));
+  k_sell_fill<<<cdiv(h->npos, 256), 256, 0, h->stream>>>(h->rowptr.as<int>(), h->ent_col.as<int>(), h->ent_eid.as<int>(),
+                                                        h->sell_row.as<int>(), h->slice_off.as<int>(),
+                                                        h->slice_width.as<int>(), h->npos, h->sell_col.as<int>(),
+                                                        h->sell_eid.as<int>(), h->sell_w2.as<double>());
+  return launch_check(h, "k_sell_fill");
 }
 
 ira_status upload_Q(ira_context* h, const double* Q, int64_t ld_q, DevBuf& dst) {
@@ -498,6 +592,10 @@ ira_status ira_create(ira_handle* out, const ira_options* opt) {
   ok = ok && h->ctl.reserve(sizeof(Ctl)) == cudaSuccess;
   ok = ok && h->partials.reserve(sizeof(double) * 8 * kRedMaxBlocks) == cudaSuccess;
   ok = ok && h->bad.reserve(sizeof(int)) == cudaSuccess;
+  int coop = 0, nb = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_persistent, kPcgThreads, 0) == cudaSuccess)
+    h->pcg_blocks_per_sm = nb;
   if (!ok) { cudaGetLastError(); ira_destroy(h); return IRA_ERR_CUDA; }
   *out = h;
   return IRA_OK;
@@ -510,7 +608,8 @@ ira_status ira_destroy(ira_handle h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (DevBuf* b : {&h->I, &h->QQ, &h->weights, &h->wres, &h->Q, &h->Q0, &h->stage, &h->rowptr, &h->ent_col,
                     &h->ent_eid, &h->ent_w2, &h->keys, &h->vals, &h->cubtmp, &h->X, &h->R, &h->Z, &h->P,
-                    &h->AP, &h->B, &h->diag, &h->dinv, &h->ctl, &h->partials, &h->bad, &h->flush})
+                    &h->AP, &h->B, &h->diag, &h->dinv, &h->ctl, &h->partials, &h->bad, &h->flush, &h->S, &h->sell_row,
+                    &h->slice_off, &h->slice_width, &h->slice_cnt, &h->sell_col, &h->sell_eid, &h->sell_w2})
     b->release();
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -537,6 +636,13 @@ ira_status ira_problem_upload(ira_handle h, int64_t m, int64_t n_total, int32_t 
   }
   IRA_TRY(upload_Q(h, Q0, ld_q, h->Q0));
   IRA_TRY(build_csr(h));
+  // SELL padding blow-up (heavy-tailed degrees) falls back to the CSR sub-warp kernels
+  h->fmt_csr = h->opt.lanes_per_row >= 2;
+  if (!h->fmt_csr) {
+    IRA_TRY(build_sell(h));
+    if (h->sell_total > 3ll * std::max(h->nnz, 1) + 64ll * kSellSigma) h->fmt_csr = true;
+  }
+  h->persistent = !h->fmt_csr && h->opt.world_size <= 1 && h->opt.solver != 1 && h->pcg_blocks_per_sm > 0;
   h->prev_cg = 0;
   h->uploaded = true;
   return IRA_OK;
@@ -582,7 +688,8 @@ ira_status ira_irls_resident(ira_handle h, int32_t cost, double sigma, int32_t m
     IRA_TRY(run_residual(h, h->Q.as<double4>(), 0));                       // :592-593
     int cg_it = 0, hit = 0;
     double rel = 0.0;
-    IRA_TRY(solve_pcg(h, &cg_it, &rel, &hit));                             // :596-612
+    if (h->persistent) IRA_TRY(solve_pcg_persistent(h));                   // :596-612
+    else IRA_TRY(solve_pcg(h, &cg_it, &rel, &hit));
     if (m > 0) {
       ProfScope ps(h, KC_WEIGHTS);
       k_weights<<<std::min(cdiv(m, 256), h->sms * 16), 256, 0, h->stream>>>(
@@ -598,6 +705,16 @@ ira_status ira_irls_resident(ira_handle h, int32_t cost, double sigma, int32_t m
     }
     IRA_TRY(fetch_ctl(h));
     score = h->h_ctl->score;
+    if (h->persistent) {
+      const Ctl& c = *h->h_ctl;
+      cg_it = c.cg_iters;
+      bool conv = true;
+      for (int k = 0; k < 3; ++k) {
+        if (c.bnorm2[k] > 0.0) rel = std::max(rel, sqrt(c.rnorm2[k] / c.bnorm2[k]));
+        if (!(c.rnorm2[k] <= c.rtol2 * c.bnorm2[k])) conv = false;
+      }
+      hit = conv ? 0 : 1;
+    }
     if (stats && iters < IRA_STATS_MAX_ITERS) {
       stats->score[iters] = score;
       stats->cg_iters[iters] = cg_it;
@@ -620,6 +737,14 @@ ira_status ira_irls_resident(ira_handle h, int32_t cost, double sigma, int32_t m
     stats->irls_iters = iters;
     stats->t_total_ms = ms;
     stats->kernel_launches = h->launches - launches0;
+    const Ctl& c = *h->h_ctl;
+    if (h->persistent && c.cyc_total > 0) {          // block 0's phase clocks -> milliseconds
+      const double ms_per_cycle = 1e-6 * (double)c.ns_total / (double)c.cyc_total;
+      stats->pcg_spmv_ms = ms_per_cycle * (double)c.cyc_spmv;
+      stats->pcg_update_ms = ms_per_cycle * (double)c.cyc_update;
+      stats->pcg_kernel_ms = 1e-6 * (double)c.ns_total;
+      stats->pcg_spmv_phases = (int32_t)std::min<long long>(c.pcg_spmv_phases, 2147483647ll);
+    }
   }
   if (rc == IRA_ERR_NONFINITE) h->err = "score became non-finite";
   return rc;

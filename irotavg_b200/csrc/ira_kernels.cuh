@@ -87,6 +87,9 @@ struct Ctl {
   int cg_max_iters;
   int done;            // 1: converged / capped; the remaining CG kernels of the chunk are no-ops
   unsigned int ticket; // last-block-done counter
+  // persistent solve only: SM-clock cycles block 0 spent in the SpMV+reduce and update phases,
+  // whole-kernel cycles and globaltimer nanoseconds (to convert cycles to time), SpMV phases run
+  long long cyc_spmv, cyc_update, cyc_total, ns_total, pcg_spmv_phases;
 };
 
 constexpr int kRedMaxBlocks = 1184;      // 148 SMs x 8: upper bound on reduction grids

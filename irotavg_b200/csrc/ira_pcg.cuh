@@ -1,0 +1,354 @@
+// Persistent (cooperative) PCG solve on a SELL-32-sigma copy of the CSR pattern.
+//
+// Why: the multi-kernel PCG of ira_kernels.cuh pays three launches and ~40 us per iteration at
+// config 3, and its sub-warp-per-row SpMV is latency bound (ncu: long_scoreboard, 46 % L1TEX).
+// Here one cooperative kernel runs the whole linear solve of one IRLS iteration
+// (replaces ls_solve, ral/l1_irls.cpp:536-556):
+//   * SELL-C-sigma, C = 32: rows are sorted by degree inside windows of 1024 rows, packed 32 to a
+//     slice, entries stored slice-column-major, so a warp reads its slice's (col, w2) streams as
+//     full 128 B / 256 B lines and every lane owns one row: no cross-lane reduction, no idle
+//     lanes beyond the (small) padding, 4 independent 32 B gathers in flight per lane;
+//   * Chronopoulos-Gear single-reduction CG: one fused grid reduction (gamma = r.u, delta = u.Au,
+//     |r|^2) and two grid barriers per iteration; alpha/beta are recomputed redundantly by every
+//     thread from block-ordered partial sums, so the iteration is deterministic;
+//   * 3 right-hand sides share every SpMV, each with its own alpha/beta.
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ira_kernels.cuh"
+
+namespace ira {
+namespace cg = cooperative_groups;
+
+constexpr int kSellC = 32;          // rows per slice (one warp)
+constexpr int kSellSigma = 1024;    // sorting window (rows)
+constexpr int kSellPad = INT32_MIN; // ent_eid marker of a padding slot
+constexpr int kPcgThreads = 1024;
+
+// ---- SELL construction ------------------------------------------------------------------------
+// One block per window: bitonic sort of (degree desc, row asc); writes the row of every sorted
+// position (-1 beyond n) and the width (max degree) of every slice.
+__global__ void __launch_bounds__(kSellSigma)
+k_sell_sort(const int* __restrict__ rowptr, int n, int* __restrict__ sell_row, int* __restrict__ slice_width,
+            int* __restrict__ slice_cnt) {
+  __shared__ unsigned long long key[kSellSigma];
+  const int t = threadIdx.x;
+  const int row = blockIdx.x * kSellSigma + t;
+  const unsigned int deg = row < n ? (unsigned int)(rowptr[row + 1] - rowptr[row]) : 0u;
+  // descending sort of this key = degree descending, then original order ascending; rows >= n last
+  key[t] = row < n ? (((unsigned long long)deg + 1ull) << 32) | (unsigned long long)(kSellSigma - 1 - t) : 0ull;
+  __syncthreads();
+  for (int k = 2; k <= kSellSigma; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int ixj = t ^ j;
+      if (ixj > t) {
+        const unsigned long long a = key[t], b = key[ixj];
+        const bool desc = (t & k) == 0;
+        if (desc ? (a < b) : (a > b)) { key[t] = b; key[ixj] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  const unsigned long long kk = key[t];
+  const int pos = blockIdx.x * kSellSigma + t;
+  const int src = kk ? blockIdx.x * kSellSigma + (kSellSigma - 1 - (int)(kk & 0xffffffffull)) : -1;
+  sell_row[pos] = src;
+  if ((t & (kSellC - 1)) == 0) {
+    const int w = kk ? (int)(kk >> 32) - 1 : 0;
+    slice_width[pos / kSellC] = w;
+    slice_cnt[pos / kSellC] = w * kSellC;
+  }
+}
+
+// Copy the CSR entries of every sorted row into its slice column-major slots.
+__global__ void __launch_bounds__(256)
+k_sell_fill(const int* __restrict__ rowptr, const int* __restrict__ ent_col, const int* __restrict__ ent_eid,
+            const int* __restrict__ sell_row, const int* __restrict__ slice_off, const int* __restrict__ slice_width,
+            int npos, int* __restrict__ sell_col, int* __restrict__ sell_eid, double* __restrict__ sell_w2) {
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= npos) return;
+  const int s = pos / kSellC, lane = pos % kSellC;
+  const int row = sell_row[pos];
+  const int width = slice_width[s];
+  const int64_t base = (int64_t)slice_off[s] + lane;
+  int e0 = 0, deg = 0;
+  if (row >= 0) { e0 = rowptr[row]; deg = rowptr[row + 1] - e0; }
+  for (int j = 0; j < width; ++j) {
+    const int64_t o = base + (int64_t)j * kSellC;
+    if (j < deg) { sell_col[o] = ent_col[e0 + j]; sell_eid[o] = ent_eid[e0 + j]; }
+    else { sell_col[o] = row >= 0 ? row : 0; sell_eid[o] = kSellPad; }   // p_r - p_r = 0, w2 = 0
+    sell_w2[o] = 0.0;
+  }
+}
+
+// ---- rhs / diagonal / per-entry weights on the SELL pattern  (ral/l1_irls.cpp:596-610) ---------
+__global__ void __launch_bounds__(256)
+k_sell_rhs(const int* __restrict__ sell_row, const int* __restrict__ slice_off, const int* __restrict__ slice_width,
+           const int* __restrict__ sell_eid, const double4* __restrict__ wres, double* __restrict__ sell_w2,
+           double4* __restrict__ B, double* __restrict__ diag, int nslices) {
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int s = gwarp; s < nslices; s += nwarps) {
+    const int row = sell_row[s * kSellC + lane];
+    const int width = slice_width[s];
+    const int64_t base = (int64_t)slice_off[s] + lane;
+    double bx = 0, by = 0, bz = 0, d = 0;
+#pragma unroll 4
+    for (int j = 0; j < width; ++j) {
+      const int64_t o = base + (int64_t)j * kSellC;
+      const int eid = sell_eid[o];
+      double w2 = 0.0;
+      if (eid != kSellPad) {
+        const bool neg = eid < 0;
+        const double4 w = ldg256(wres + (neg ? ~eid : eid));
+        w2 = w.w;
+        d += w2;
+        const double sg = neg ? -w2 : w2;
+        bx += sg * w.x; by += sg * w.y; bz += sg * w.z;
+      }
+      sell_w2[o] = w2;
+    }
+    if (row >= 0) {
+      st256(B + row, make_double4(bx, by, bz, 0.0));
+      diag[row] = d;
+    }
+  }
+}
+
+// One lane's row of (A^T D^2 A) v: sum_e w2_e (v_row - v_col(e)) over the slice-column-major slots
+// base, base+32, ...; 4 independent 32 B gathers in flight per lane.
+__device__ __forceinline__ void sell_row_apply(const int* __restrict__ sell_col, const double* __restrict__ sell_w2,
+                                               const double4* V, int64_t base, int width, const double4 u,
+                                               double& ax, double& ay, double& az) {
+  ax = 0.0; ay = 0.0; az = 0.0;
+  int j = 0;
+  for (; j + 4 <= width; j += 4) {
+    int c[4]; double w2[4]; double4 uc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t o = base + (int64_t)(j + q) * kSellC;
+      c[q] = __ldg(sell_col + o);
+      w2[q] = __ldg(sell_w2 + o);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) uc[q] = ld256(V + c[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      ax += w2[q] * (u.x - uc[q].x); ay += w2[q] * (u.y - uc[q].y); az += w2[q] * (u.z - uc[q].z);
+    }
+  }
+  for (; j < width; ++j) {
+    const int64_t o = base + (int64_t)j * kSellC;
+    const int c = __ldg(sell_col + o);
+    const double w2 = __ldg(sell_w2 + o);
+    const double4 uc = ld256(V + c);
+    ax += w2 * (u.x - uc.x); ay += w2 * (u.y - uc.y); az += w2 * (u.z - uc.z);
+  }
+}
+
+// Stand-alone SELL SpMV (multi-kernel / sharded path and the roofline probe): AP = (A^T D^2 A) P,
+// optionally fused with p.Ap and alpha exactly like k_spmv.
+template <bool FUSE_DOT>
+__global__ void __launch_bounds__(256)
+k_spmv_sell(const int* __restrict__ sell_row, const int* __restrict__ slice_off, const int* __restrict__ slice_width,
+            const int* __restrict__ sell_col, const double* __restrict__ sell_w2, const double4* __restrict__ P,
+            double4* __restrict__ AP, int nslices, Ctl* ctl, double* partials) {
+  if (ctl->done) return;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  double dot[3] = {0, 0, 0};
+  for (int s = gwarp; s < nslices; s += nwarps) {
+    const int row = sell_row[s * kSellC + lane];
+    const int width = slice_width[s];
+    const int64_t base = (int64_t)slice_off[s] + lane;
+    const double4 u = row >= 0 ? ld256(P + row) : make_double4(0, 0, 0, 0);
+    double ax, ay, az;
+    sell_row_apply(sell_col, sell_w2, P, base, width, u, ax, ay, az);
+    if (row >= 0) {
+      st256(AP + row, make_double4(ax, ay, az, 0.0));
+      if (FUSE_DOT) { dot[0] += u.x * ax; dot[1] += u.y * ay; dot[2] += u.z * az; }
+    }
+  }
+  if (FUSE_DOT) {
+    __shared__ double sm[3 * 32];
+    __shared__ int flag;
+    if (grid_reduce_last<3>(dot, partials, &ctl->ticket, sm, &flag) && threadIdx.x == 0) {
+      for (int c = 0; c < 3; ++c) ctl->alpha[c] = dot[c] > 0.0 ? ctl->rz[c] / dot[c] : 0.0;
+    }
+  }
+}
+
+// ---- the persistent solve ----------------------------------------------------------------------
+struct PcgParams {
+  int n, nslices, max_iters;
+  double rtol2;
+  const int* sell_row; const int* slice_off; const int* slice_width;
+  const int* sell_col; const double* sell_w2;
+  const double4* B; const double* diag;
+  double4 *X, *R, *U, *W, *P, *S;
+  double* dinv;
+  double* partials;      // [gridDim.x][kPcgNV]
+  Ctl* ctl;
+};
+constexpr int kPcgNV = 9;
+
+// Block-ordered grid reduction through one grid barrier; every thread of every block returns the
+// same totals (bitwise), so loop control and alpha/beta stay uniform without a broadcast.
+__device__ __forceinline__ void pcg_grid_reduce(double (&v)[kPcgNV], double* partials, cg::grid_group& grid,
+                                                double* red /* [kPcgNV*32] */, double* tot /* [kPcgNV] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kPcgNV; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (lane == 0) red[k * 32 + warp] = v[k];
+  }
+  __syncthreads();
+  if (warp < kPcgNV) {
+    double t = lane < nw ? red[warp * 32 + lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) __stcg(&partials[blockIdx.x * kPcgNV + warp], t);
+  }
+  grid.sync();
+  if (warp < kPcgNV) {
+    double t = 0.0;
+    for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(&partials[b * kPcgNV + warp]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) tot[warp] = t;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kPcgNV; ++k) v[k] = tot[k];
+}
+
+__global__ void __launch_bounds__(kPcgThreads, 1)
+k_pcg_persistent(const PcgParams p) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double red[kPcgNV * 32];
+  __shared__ double tot[kPcgNV];
+  const int lane = threadIdx.x & 31;
+  const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  double v[kPcgNV];
+
+  // ---- start: x = 0, r = b, u = M^-1 r, p = s = 0; |b|^2 ---------------------------------------
+#pragma unroll
+  for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
+  for (int s = gwarp; s < p.nslices; s += nwarps) {
+    const int row = p.sell_row[s * kSellC + lane];
+    if (row >= 0) {
+      const double4 b = ldg256(p.B + row);
+      const double d = p.diag[row];
+      const double di = d > 0.0 ? 1.0 / d : 0.0;
+      p.dinv[row] = di;
+      const double4 z4 = make_double4(0, 0, 0, 0);
+      st256(p.X + row, z4); st256(p.P + row, z4); st256(p.S + row, z4);
+      st256(p.R + row, b);
+      st256(p.U + row, make_double4(di * b.x, di * b.y, di * b.z, 0.0));
+      v[0] += b.x * b.x; v[1] += b.y * b.y; v[2] += b.z * b.z;
+    }
+  }
+  pcg_grid_reduce(v, p.partials, grid, red, tot);     // also publishes U to the whole grid
+  // loop-carried scalars live in shared memory (thread 0 updates them) to keep 1024 threads at 64 regs
+  __shared__ double sc_bb[3], sc_go[3], sc_ao[3], sc_a[3], sc_b[3], sc_rr[3];
+  __shared__ int sc_stop;
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < 3; ++c) { sc_bb[c] = v[c]; sc_rr[c] = v[c]; sc_go[c] = 1.0; sc_ao[c] = 1.0; }
+    sc_stop = !(v[0] > 0.0 || v[1] > 0.0 || v[2] > 0.0);   // zero right-hand side: x = 0
+  }
+  __syncthreads();
+  int it = 0;
+  // phase clocks of block 0 (every block runs the same phases between the same barriers)
+  const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+  long long c_spmv = 0, c_upd = 0, c_mark = 0, c_begin = 0;
+  unsigned long long ns_begin = 0;
+  if (timer) { c_begin = c_mark = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_begin)); }
+
+  while (!sc_stop) {
+    // ---- w = A u (SpMV), gamma = r.u, delta = u.w, |r|^2 ---------------------------------------
+#pragma unroll
+    for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
+    for (int s = gwarp; s < p.nslices; s += nwarps) {
+      const int row = p.sell_row[s * kSellC + lane];
+      const int width = p.slice_width[s];
+      const int64_t base = (int64_t)p.slice_off[s] + lane;
+      const double4 u = row >= 0 ? ld256(p.U + row) : make_double4(0, 0, 0, 0);
+      double ax, ay, az;
+      sell_row_apply(p.sell_col, p.sell_w2, p.U, base, width, u, ax, ay, az);
+      if (row >= 0) {
+        st256(p.W + row, make_double4(ax, ay, az, 0.0));
+        const double4 r = ld256(p.R + row);
+        v[0] += r.x * u.x; v[1] += r.y * u.y; v[2] += r.z * u.z;
+        v[3] += u.x * ax;  v[4] += u.y * ay;  v[5] += u.z * az;
+        v[6] += r.x * r.x; v[7] += r.y * r.y; v[8] += r.z * r.z;
+      }
+    }
+    pcg_grid_reduce(v, p.partials, grid, red, tot);
+    if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; }
+    // ---- Chronopoulos-Gear coefficients (thread 0; identical in every block) ---------------------
+    if (threadIdx.x == 0) {
+      bool conv = true;
+      for (int c = 0; c < 3; ++c) {
+        sc_rr[c] = v[6 + c];
+        if (!(v[6 + c] <= p.rtol2 * sc_bb[c])) conv = false;
+      }
+      if (conv || it >= p.max_iters) {
+        sc_stop = 1;
+      } else {
+        for (int c = 0; c < 3; ++c) {
+          const double gam = v[c], del = v[3 + c];
+          double beta = 0.0, den = del;
+          if (it > 0) {
+            beta = sc_go[c] > 0.0 ? gam / sc_go[c] : 0.0;
+            if (sc_ao[c] != 0.0) den = del - beta * gam / sc_ao[c];
+          }
+          const double alpha = den > 0.0 ? gam / den : 0.0;
+          sc_go[c] = gam; sc_ao[c] = alpha; sc_a[c] = alpha; sc_b[c] = beta;
+        }
+      }
+    }
+    __syncthreads();
+    if (sc_stop) break;
+    const double a0 = sc_a[0], a1 = sc_a[1], a2 = sc_a[2], b0 = sc_b[0], b1 = sc_b[1], b2 = sc_b[2];
+    // ---- p = u + beta p; s = w + beta s; x += alpha p; r -= alpha s; u = M^-1 r ----------------------
+    for (int s = gwarp; s < p.nslices; s += nwarps) {
+      const int row = p.sell_row[s * kSellC + lane];
+      if (row >= 0) {
+        const double4 u = ld256(p.U + row), w = ld256(p.W + row);
+        double4 pp = ld256(p.P + row), ss = ld256(p.S + row);
+        pp.x = u.x + b0 * pp.x; pp.y = u.y + b1 * pp.y; pp.z = u.z + b2 * pp.z;
+        ss.x = w.x + b0 * ss.x; ss.y = w.y + b1 * ss.y; ss.z = w.z + b2 * ss.z;
+        st256(p.P + row, pp); st256(p.S + row, ss);
+        double4 x = ld256(p.X + row), r = ld256(p.R + row);
+        const double di = p.dinv[row];
+        x.x += a0 * pp.x; x.y += a1 * pp.y; x.z += a2 * pp.z;
+        r.x -= a0 * ss.x; r.y -= a1 * ss.y; r.z -= a2 * ss.z;
+        st256(p.X + row, x); st256(p.R + row, r);
+        st256(p.U + row, make_double4(di * r.x, di * r.y, di * r.z, 0.0));
+      }
+    }
+    ++it;
+    grid.sync();                                        // new u visible before the next gathers
+    if (timer) { const long long c = clock64(); c_upd += c - c_mark; c_mark = c; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    p.ctl->cg_iters = it;
+    for (int c = 0; c < 3; ++c) { p.ctl->bnorm2[c] = sc_bb[c]; p.ctl->rnorm2[c] = sc_rr[c]; }
+    p.ctl->done = 1;
+    unsigned long long ns_end;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_end));
+    p.ctl->cyc_spmv += c_spmv;
+    p.ctl->cyc_update += c_upd;
+    p.ctl->cyc_total += clock64() - c_begin;
+    p.ctl->ns_total += (long long)(ns_end - ns_begin);
+    p.ctl->pcg_spmv_phases += c_spmv > 0 ? it + 1 : 0;
+  }
+}
+
+}  // namespace ira

@@ -232,6 +232,28 @@ def test_large_angle_identity_start(solver):
     assert O.geodesic_rms(Q, ref.Q, g.f) <= RMS_TOL
 
 
+@pytest.mark.parametrize("solver_kind", [1, 2])
+@pytest.mark.parametrize("maker", ["random", "kitti", "tiny"])
+def test_solver_variants(built_lib, solver_kind, maker):
+    """solver 1 = one kernel per CG step (SELL SpMV, host-polled), 2 = persistent cooperative PCG."""
+    import irotavg_b200 as ira
+    if maker == "random":
+        g = G.small_graph(n=3000, extra=30000, sigma_n=0.03, outlier_frac=0.1, seed=31, f=2, fixed_anywhere=True)
+    elif maker == "kitti":
+        g = G.kitti_like_graph(n=1500, m=16000)
+    else:
+        g = G.small_graph(n=14, extra=26, sigma_n=0.01, seed=4, f=4)
+    ref = O.irls(g.QQ, g.I, None, O.GEMAN_MCCLURE, SIGMA, g.Q0, g.f, 6, -1.0, solver="direct")
+    with ira.Solver(solver=solver_kind) as s:
+        Q, w, info = s.irls(g.QQ, g.I, None, O.GEMAN_MCCLURE, SIGMA, g.Q0, g.f, 6, -1.0)
+        Q2, w2, _ = s.irls(g.QQ, g.I, None, O.GEMAN_MCCLURE, SIGMA, g.Q0, g.f, 6, -1.0)
+    assert info.cg_hit_max == 0 and all(k > 0 for k in info.cg_iters)
+    assert np.allclose(info.scores, ref.scores, rtol=1e-6, atol=1e-12)
+    assert O.geodesic_rms(Q, ref.Q, g.f) <= RMS_TOL
+    assert np.allclose(w, ref.weights, rtol=1e-5, atol=1e-8)
+    assert np.array_equal(Q, Q2) and np.array_equal(w, w2)          # bitwise repeatable
+
+
 @pytest.mark.parametrize("lpr", [2, 4, 8, 16, 32])
 def test_lanes_per_row_variants(built_lib, lpr):
     import irotavg_b200 as ira

@@ -39,5 +39,8 @@ out = {"graph": g.name, "cost": a.cost, "iters": info.iters, "device_ms": info.d
        "launches": info.kernel_launches, "cg_iters": info.cg_iters, "cg_total": sum(info.cg_iters),
        "scores": info.scores[-3:], "cg_hit_max": info.cg_hit_max}
 for k, v in info.profile.items():
-    out[k] = {"ms": round(v["ms"], 4), "launches": v["launches"], "us_per_launch": round(1000 * v["ms"] / v["launches"], 3)}
+    if "launches" in v:
+        out[k] = {"ms": round(v["ms"], 4), "launches": v["launches"], "us_per_launch": round(1000 * v["ms"] / v["launches"], 3)}
+    else:
+        out[k] = {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()}
 print(json.dumps(out))
