@@ -64,7 +64,8 @@ typedef struct ira_options {
   int32_t profile;         /* 1: record CUDA-event timings per kernel class into ira_stats        */
   int32_t solver;          /* PCG driver: 0 = auto (persistent cooperative kernel on one GPU), 1 = one
                               kernel per CG step with host-polled convergence, 2 = persistent       */
-  int32_t reserved[6];
+  int32_t spmv_variant;    /* experiment knob: gather flavour / unroll of the SELL SpMV (0 = default)  */
+  int32_t reserved[5];
 } ira_options;
 
 #define IRA_STATS_MAX_ITERS 256

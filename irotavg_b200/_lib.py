@@ -34,7 +34,8 @@ class Options(C.Structure):
         ("rank", C.c_int32),
         ("profile", C.c_int32),
         ("solver", C.c_int32),
-        ("reserved", C.c_int32 * 6),
+        ("spmv_variant", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 

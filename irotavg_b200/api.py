@@ -80,7 +80,7 @@ class Solver:
 
     def __init__(self, device: int = -1, cg_rtol: float | None = None, cg_max_iters: int | None = None,
                  cg_check_every: int | None = None, lanes_per_row: int = 0, world_size: int = 1,
-                 rank: int = 0, profile: bool = False, solver: int = 0):
+                 rank: int = 0, profile: bool = False, solver: int = 0, spmv_variant: int = 0):
         self._lib = _lib.load()
         opt = Options()
         self._check(self._lib.ira_options_default(C.byref(opt)), None)
@@ -96,6 +96,7 @@ class Solver:
         opt.rank = rank
         opt.profile = int(profile)
         opt.solver = solver
+        opt.spmv_variant = spmv_variant
         self.options = opt
         self._h = C.c_void_p()
         self._check(self._lib.ira_create(C.byref(self._h), C.byref(opt)), None)

@@ -230,8 +230,9 @@ ira_status run_rhs_t(ira_context* h) {
       h->B.as<double4>(), h->diag.as<double>(), h->n);
   return launch_check(h, "k_rhs_diag");
 }
-int grid_slices(const ira_context* h) {
-  return std::max(1, std::min(cdiv((int64_t)h->nslices * 32, 256), h->sms * 8));
+int grid_slices(const ira_context* h) {      // a multiple of the SM count: slices are dealt round-robin
+  const int per_sm = std::max(1, std::min(8, cdiv(cdiv((int64_t)h->nslices * 32, 256), h->sms)));
+  return h->sms * per_sm;
 }
 
 ira_status run_rhs(ira_context* h) {
@@ -270,16 +271,28 @@ ira_status run_spmv_t(ira_context* h, bool fuse) {
 ira_status run_spmv(ira_context* h, bool fuse) {
   ProfScope ps(h, KC_SPMV);
   if (!h->fmt_csr) {
-    if (fuse)
-      k_spmv_sell<true><<<grid_slices(h), 256, 0, h->stream>>>(
-          h->sell_row.as<int>(), h->slice_off.as<int>(), h->slice_width.as<int>(), h->sell_col.as<int>(),
-          h->sell_w2.as<double>(), h->P.as<double4>(), h->AP.as<double4>(), h->nslices, h->ctl.as<Ctl>(),
-          h->partials.as<double>());
-    else
-      k_spmv_sell<false><<<grid_slices(h), 256, 0, h->stream>>>(
-          h->sell_row.as<int>(), h->slice_off.as<int>(), h->slice_width.as<int>(), h->sell_col.as<int>(),
-          h->sell_w2.as<double>(), h->P.as<double4>(), h->AP.as<double4>(), h->nslices, h->ctl.as<Ctl>(),
-          h->partials.as<double>());
+#define IRA_SPMV_SELL(FUSE, V, U)                                                                          \
+  k_spmv_sell<FUSE, V, U><<<grid_slices(h), 256, 0, h->stream>>>(                                          \
+      h->sell_row.as<int>(), h->slice_off.as<int>(), h->slice_width.as<int>(), h->sell_col.as<int>(),      \
+      h->sell_w2.as<double>(), h->P.as<double4>(), h->AP.as<double4>(), h->nslices, h->ctl.as<Ctl>(),      \
+      h->partials.as<double>())
+    const int var = h->opt.spmv_variant;
+    if (fuse) {
+      switch (var) {
+        case 1: IRA_SPMV_SELL(true, 1, 4); break;
+        case 2: IRA_SPMV_SELL(true, 2, 4); break;
+        case 3: IRA_SPMV_SELL(true, 0, 8); break;
+        case 4: IRA_SPMV_SELL(true, 1, 8); break;
+        case 5: IRA_SPMV_SELL(true, 2, 8); break;
+        default: IRA_SPMV_SELL(true, 0, 4); break;
+      }
+    } else {
+      switch (var) {
+        case 1: case 4: IRA_SPMV_SELL(false, 1, 4); break;
+        default: IRA_SPMV_SELL(false, 0, 4); break;
+      }
+    }
+#undef IRA_SPMV_SELL
     return launch_check(h, "k_spmv_sell");
   }
   switch (h->lpr) {
@@ -355,11 +368,19 @@ ira_status solve_pcg_persistent(ira_context* h) {
   pp.X = h->X.as<double4>(); pp.R = h->R.as<double4>(); pp.U = h->Z.as<double4>(); pp.W = h->AP.as<double4>();
   pp.P = h->P.as<double4>(); pp.S = h->S.as<double4>();
   pp.dinv = h->dinv.as<double>(); pp.partials = h->partials.as<double>(); pp.ctl = h->ctl.as<Ctl>();
-  const int warps_per_block = kPcgThreads / 32;
-  const int grid = std::max(1, std::min(cdiv(h->nslices, warps_per_block), h->sms * h->pcg_blocks_per_sm));
+  // one block per SM (slices are dealt round-robin over blocks); tiny graphs use fewer blocks so that
+  // the grid barrier has fewer participants
+  const int grid = std::max(1, std::min(h->nslices, h->sms * h->pcg_blocks_per_sm));
   void* args[] = {(void*)&pp};
   ProfScope ps(h, KC_PCG);
-  IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_pcg_persistent, dim3(grid), dim3(kPcgThreads), args, 0, h->stream));
+  void* fn = nullptr;
+  switch (h->opt.spmv_variant) {
+    case 1: fn = (void*)k_pcg_persistent<1, 4>; break;
+    case 3: fn = (void*)k_pcg_persistent<0, 8>; break;
+    case 4: fn = (void*)k_pcg_persistent<1, 8>; break;
+    default: fn = (void*)k_pcg_persistent<0, 4>; break;
+  }
+  IRA_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPcgThreads), args, 0, h->stream));
   h->launches++;
   return IRA_OK;
 }
@@ -594,7 +615,7 @@ ira_status ira_create(ira_handle* out, const ira_options* opt) {
   ok = ok && h->bad.reserve(sizeof(int)) == cudaSuccess;
   int coop = 0, nb = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-  if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_persistent, kPcgThreads, 0) == cudaSuccess)
+  if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_persistent<0, 8>, kPcgThreads, 0) == cudaSuccess)
     h->pcg_blocks_per_sm = nb;
   if (!ok) { cudaGetLastError(); ira_destroy(h); return IRA_ERR_CUDA; }
   *out = h;

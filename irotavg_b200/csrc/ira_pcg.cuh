@@ -25,7 +25,7 @@ namespace cg = cooperative_groups;
 constexpr int kSellC = 32;          // rows per slice (one warp)
 constexpr int kSellSigma = 1024;    // sorting window (rows)
 constexpr int kSellPad = INT32_MIN; // ent_eid marker of a padding slot
-constexpr int kPcgThreads = 1024;
+constexpr int kPcgThreads = 768;   // 24 warps, <= 85 registers per thread
 
 // ---- SELL construction ------------------------------------------------------------------------
 // One block per window: bitonic sort of (degree desc, row asc); writes the row of every sorted
@@ -56,7 +56,7 @@ k_sell_sort(const int* __restrict__ rowptr, int n, int* __restrict__ sell_row, i
   const int src = kk ? blockIdx.x * kSellSigma + (kSellSigma - 1 - (int)(kk & 0xffffffffull)) : -1;
   sell_row[pos] = src;
   if ((t & (kSellC - 1)) == 0) {
-    const int w = kk ? (int)(kk >> 32) - 1 : 0;
+    const int w = kk ? (((int)(kk >> 32) - 1 + 3) & ~3) : 0;      // multiple of 4 (sell_row_apply)
     slice_width[pos / kSellC] = w;
     slice_cnt[pos / kSellC] = w * kSellC;
   }
@@ -118,56 +118,118 @@ k_sell_rhs(const int* __restrict__ sell_row, const int* __restrict__ slice_off, 
   }
 }
 
+// Gather flavours (experiment knob, ira_options.spmv_variant): 0 = plain coherent ld.global (L1
+// allocating), 1 = ld.global.L1::no_allocate (coherent at L2; the gathered vector has ~5 % L1 hit rate
+// on a random graph, so allocation only churns the cache), 2 = ld.global.nc (read-only path; not legal
+// inside the persistent kernel, where the vector is rewritten between barriers).
+template <int V>
+__device__ __forceinline__ double4 gather256(const double4* p) {
+  double4 v;
+  if (V == 1)
+    asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p) : "memory");
+  else if (V == 2)
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  else
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
 // One lane's row of (A^T D^2 A) v: sum_e w2_e (v_row - v_col(e)) over the slice-column-major slots
-// base, base+32, ...; 4 independent 32 B gathers in flight per lane.
+// base, base+32, ...  Slice widths are multiples of 4 (padding slots have col = row, w2 = 0).
+// Software pipelined: the (col, w2) of batch k+1 are requested before batch k's gathers are
+// consumed, so the dependent chain per batch is one gather latency, with 4 (or 8) independent 32 B
+// gathers in flight per lane.
+template <int V, int UNR>
 __device__ __forceinline__ void sell_row_apply(const int* __restrict__ sell_col, const double* __restrict__ sell_w2,
-                                               const double4* V, int64_t base, int width, const double4 u,
+                                               const double4* V_, int64_t base, int width, const double4 u,
                                                double& ax, double& ay, double& az) {
   ax = 0.0; ay = 0.0; az = 0.0;
+  if (width <= 0) return;
+  int c[4]; double w2[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int64_t o = base + (int64_t)q * kSellC;
+    c[q] = __ldg(sell_col + o);
+    w2[q] = __ldg(sell_w2 + o);
+  }
   int j = 0;
-  for (; j + 4 <= width; j += 4) {
-    int c[4]; double w2[4]; double4 uc[4];
+  if (UNR == 8) {
+    for (; j + 8 <= width; j += 8) {
+      int c2[4]; double w22[4]; double4 ua[4], ub[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int64_t o = base + (int64_t)(j + q) * kSellC;
-      c[q] = __ldg(sell_col + o);
-      w2[q] = __ldg(sell_w2 + o);
+      for (int q = 0; q < 4; ++q) {
+        const int64_t o = base + (int64_t)(j + 4 + q) * kSellC;
+        c2[q] = __ldg(sell_col + o);
+        w22[q] = __ldg(sell_w2 + o);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ua[q] = gather256<V>(V_ + c[q]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ub[q] = gather256<V>(V_ + c2[q]);
+      int cn[4] = {0, 0, 0, 0}; double wn[4] = {0, 0, 0, 0};
+      if (j + 8 < width) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int64_t o = base + (int64_t)(j + 8 + q) * kSellC;
+          cn[q] = __ldg(sell_col + o);
+          wn[q] = __ldg(sell_w2 + o);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        ax += w2[q] * (u.x - ua[q].x); ay += w2[q] * (u.y - ua[q].y); az += w2[q] * (u.z - ua[q].z);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        ax += w22[q] * (u.x - ub[q].x); ay += w22[q] * (u.y - ub[q].y); az += w22[q] * (u.z - ub[q].z);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { c[q] = cn[q]; w2[q] = wn[q]; }
     }
+  }
+  for (; j < width; j += 4) {
+    double4 uc[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) uc[q] = ld256(V + c[q]);
+    for (int q = 0; q < 4; ++q) uc[q] = gather256<V>(V_ + c[q]);
+    int cn[4] = {0, 0, 0, 0}; double wn[4] = {0, 0, 0, 0};
+    if (j + 4 < width) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t o = base + (int64_t)(j + 4 + q) * kSellC;
+        cn[q] = __ldg(sell_col + o);
+        wn[q] = __ldg(sell_w2 + o);
+      }
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       ax += w2[q] * (u.x - uc[q].x); ay += w2[q] * (u.y - uc[q].y); az += w2[q] * (u.z - uc[q].z);
     }
-  }
-  for (; j < width; ++j) {
-    const int64_t o = base + (int64_t)j * kSellC;
-    const int c = __ldg(sell_col + o);
-    const double w2 = __ldg(sell_w2 + o);
-    const double4 uc = ld256(V + c);
-    ax += w2 * (u.x - uc.x); ay += w2 * (u.y - uc.y); az += w2 * (u.z - uc.z);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { c[q] = cn[q]; w2[q] = wn[q]; }
   }
 }
 
 // Stand-alone SELL SpMV (multi-kernel / sharded path and the roofline probe): AP = (A^T D^2 A) P,
-// optionally fused with p.Ap and alpha exactly like k_spmv.
-template <bool FUSE_DOT>
+// optionally fused with p.Ap and alpha exactly like k_spmv.  Slices are dealt to blocks round-robin
+// (slice s -> block s % gridDim.x) so that every SM gets the same number of slices.
+template <bool FUSE_DOT, int V, int UNR>
 __global__ void __launch_bounds__(256)
 k_spmv_sell(const int* __restrict__ sell_row, const int* __restrict__ slice_off, const int* __restrict__ slice_width,
             const int* __restrict__ sell_col, const double* __restrict__ sell_w2, const double4* __restrict__ P,
             double4* __restrict__ AP, int nslices, Ctl* ctl, double* partials) {
   if (ctl->done) return;
   const int lane = threadIdx.x & 31;
-  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   double dot[3] = {0, 0, 0};
-  for (int s = gwarp; s < nslices; s += nwarps) {
+  for (int s = blockIdx.x + gridDim.x * warp; s < nslices; s += gridDim.x * wpb) {
     const int row = sell_row[s * kSellC + lane];
     const int width = slice_width[s];
     const int64_t base = (int64_t)slice_off[s] + lane;
-    const double4 u = row >= 0 ? ld256(P + row) : make_double4(0, 0, 0, 0);
+    const double4 u = row >= 0 ? gather256<V>(P + row) : make_double4(0, 0, 0, 0);
     double ax, ay, az;
-    sell_row_apply(sell_col, sell_w2, P, base, width, u, ax, ay, az);
+    sell_row_apply<V, UNR>(sell_col, sell_w2, P, base, width, u, ax, ay, az);
     if (row >= 0) {
       st256(AP + row, make_double4(ax, ay, az, 0.0));
       if (FUSE_DOT) { dot[0] += u.x * ax; dot[1] += u.y * ay; dot[2] += u.z * az; }
@@ -227,13 +289,15 @@ __device__ __forceinline__ void pcg_grid_reduce(double (&v)[kPcgNV], double* par
   for (int k = 0; k < kPcgNV; ++k) v[k] = tot[k];
 }
 
+template <int V, int UNR>
 __global__ void __launch_bounds__(kPcgThreads, 1)
 k_pcg_persistent(const PcgParams p) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double red[kPcgNV * 32];
   __shared__ double tot[kPcgNV];
   const int lane = threadIdx.x & 31;
-  const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // slices are dealt to blocks round-robin: every SM owns the same number of slices (+-1)
+  const int gwarp = blockIdx.x + gridDim.x * (threadIdx.x >> 5);
   const int nwarps = gridDim.x * (blockDim.x >> 5);
   double v[kPcgNV];
 
@@ -280,7 +344,7 @@ k_pcg_persistent(const PcgParams p) {
       const int64_t base = (int64_t)p.slice_off[s] + lane;
       const double4 u = row >= 0 ? ld256(p.U + row) : make_double4(0, 0, 0, 0);
       double ax, ay, az;
-      sell_row_apply(p.sell_col, p.sell_w2, p.U, base, width, u, ax, ay, az);
+      sell_row_apply<V, UNR>(p.sell_col, p.sell_w2, p.U, base, width, u, ax, ay, az);
       if (row >= 0) {
         st256(p.W + row, make_double4(ax, ay, az, 0.0));
         const double4 r = ld256(p.R + row);

@@ -28,10 +28,13 @@ ap.add_argument("--no-profile", action="store_true")
 ap.add_argument("--lpr", type=int, default=0)
 ap.add_argument("--solver", type=int, default=0)
 ap.add_argument("--check-every", type=int, default=None)
+ap.add_argument("--variant", type=int, default=0)
+ap.add_argument("--time-kernels", action="store_true")
 a = ap.parse_args()
 
 g = G.kitti_like_graph() if a.kitti else G.random_graph(n=a.n, m=a.m)
-s = ira.Solver(profile=not a.no_profile, lanes_per_row=a.lpr, solver=a.solver, cg_check_every=a.check_every)
+s = ira.Solver(profile=not a.no_profile, lanes_per_row=a.lpr, solver=a.solver, cg_check_every=a.check_every,
+               spmv_variant=a.variant)
 s.upload(g.QQ, g.I, g.Q0, g.f)
 for _ in range(a.reps):
     info = s.irls_resident(COSTS[a.cost], 5 * np.pi / 180, a.iters, -1.0)
@@ -43,4 +46,7 @@ for k, v in info.profile.items():
         out[k] = {"ms": round(v["ms"], 4), "launches": v["launches"], "us_per_launch": round(1000 * v["ms"] / v["launches"], 3)}
     else:
         out[k] = {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()}
+if a.time_kernels:
+    out["kernel_us_warm"] = {nm: round(s.time_kernel(k, 50, False), 3) for k, nm in enumerate(["residual", "spmv", "rhs", "weights", "update", "cg_update"])}
+    out["kernel_us_cold"] = {nm: round(s.time_kernel(k, 20, True), 3) for k, nm in enumerate(["residual", "spmv", "rhs", "weights", "update", "cg_update"])}
 print(json.dumps(out))
