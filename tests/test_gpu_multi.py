@@ -1,0 +1,60 @@
+"""Multi-GPU (one process per GPU, NCCL): edge-sharded irls() equals the single-GPU / oracle result.
+Needs >= 2 GPUs (`gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`); skipped on a
+1-GPU box."""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    import numpy as np, torch, torch.distributed as dist
+    sys.path.insert(0, os.environ["IRA_ROOT"])
+    import irotavg_b200 as ira
+    from irotavg_b200.sharding import edge_shard, broadcast_unique_id
+    from oracle import graphs as G, irls_oracle as O
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    g = G.small_graph(n=3000, extra=30000, sigma_n=0.03, outlier_frac=0.1, seed=41, f=2, fixed_anywhere=True)
+    sigma = 5 * np.pi / 180
+    lo, hi = edge_shard(g.m, world, rank)
+    s = ira.Solver(device=lr, world_size=world, rank=rank)
+    s.comm_init(broadcast_unique_id(dist, ira.Solver, rank, device="cuda"))
+    ok = True
+    for cost in (O.L1, O.GEMAN_MCCLURE):
+        Q, w, info = s.irls(g.QQ[lo:hi], g.I[lo:hi], None, cost, sigma, g.Q0, g.f, 6, -1.0)
+        ref = O.irls(g.QQ, g.I, None, cost, sigma, g.Q0, g.f, 6, -1.0, solver="direct")
+        rms = O.geodesic_rms(Q, ref.Q, g.f)
+        wok = np.allclose(w, ref.weights[lo:hi], rtol=1e-5, atol=1e-8)
+        t = torch.from_numpy(np.ascontiguousarray(Q)).cuda()
+        t0 = t.clone(); dist.broadcast(t0, 0)
+        same = bool(torch.equal(t, t0))                  # replicas are bitwise identical across ranks
+        print(f"rank {rank} cost {cost} rms {rms:.2e} weights {wok} identical {same} comm {info.profile.get('comm')}", flush=True)
+        ok = ok and rms <= 1e-8 and wok and same and info.cg_hit_max == 0
+    s.close()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+""")
+
+
+def test_two_rank_sharded_irls(tmp_path, built_lib):
+    import irotavg_b200 as ira
+    if ira.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, IRA_ROOT=ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script)]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
