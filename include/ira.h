@@ -56,6 +56,10 @@ typedef struct ira_options {
   int32_t device;          /* CUDA ordinal; -1 = current device                                   */
   int32_t cg_max_iters;    /* hard cap per linear solve                                           */
   double  cg_rtol;         /* stop when ||r_c|| <= cg_rtol * ||b_c|| for each of the 3 columns    */
+  double  pair_theta;      /* block-Jacobi pairing threshold: nodes v,u whose edge has strength
+                              w2_vu / sqrt(d_v d_u) >= pair_theta and who are each other's strongest
+                              neighbour are preconditioned together (2x2 blocks, as an additive
+                              coarse correction); 0 = plain Jacobi.  Default 0.2                  */
   int32_t cg_check_every;  /* host polls the device-side convergence flag every this many iters   */
   int32_t lanes_per_row;   /* 0 = SELL-32 thread-per-row kernels (default); 2..32 = CSR kernels
                               with that many lanes per row (forces solver 1)                       */

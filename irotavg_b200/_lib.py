@@ -28,6 +28,7 @@ class Options(C.Structure):
         ("device", C.c_int32),
         ("cg_max_iters", C.c_int32),
         ("cg_rtol", C.c_double),
+        ("pair_theta", C.c_double),
         ("cg_check_every", C.c_int32),
         ("lanes_per_row", C.c_int32),
         ("world_size", C.c_int32),

@@ -80,7 +80,8 @@ class Solver:
 
     def __init__(self, device: int = -1, cg_rtol: float | None = None, cg_max_iters: int | None = None,
                  cg_check_every: int | None = None, lanes_per_row: int = 0, world_size: int = 1,
-                 rank: int = 0, profile: bool = False, solver: int = 0, spmv_variant: int = 0):
+                 rank: int = 0, profile: bool = False, solver: int = 0, spmv_variant: int = 0,
+                 pair_theta: float | None = None):
         self._lib = _lib.load()
         opt = Options()
         self._check(self._lib.ira_options_default(C.byref(opt)), None)
@@ -97,6 +98,8 @@ class Solver:
         opt.profile = int(profile)
         opt.solver = solver
         opt.spmv_variant = spmv_variant
+        if pair_theta is not None:
+            opt.pair_theta = pair_theta
         self.options = opt
         self._h = C.c_void_p()
         self._check(self._lib.ira_create(C.byref(self._h), C.byref(opt)), None)

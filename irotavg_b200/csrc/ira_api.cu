@@ -88,6 +88,7 @@ struct ira_context {
   DevBuf X, R, Z, P, AP, B, diag, dinv, S;
   // SELL-32-sigma copy of the pattern (ira_pcg.cuh)
   DevBuf sell_row, slice_off, slice_width, slice_cnt, sell_col, sell_eid, sell_w2;
+  DevBuf pair_key, pair_w2, mate, pinv, npairs;
   int nslices = 0, npos = 0;
   int64_t sell_total = 0;
   bool fmt_csr = false;      // multi-kernel path on the CSR sub-warp kernels (lanes_per_row set)
@@ -357,9 +358,30 @@ ira_status fetch_ctl(ira_context* h) {
 // One linear step as ONE cooperative kernel (ira_pcg.cuh); nothing is read back here - the
 // iteration count and residual norms stay in the device control block until the IRLS iteration's
 // single host synchronisation.
+// Pairwise block-Jacobi set-up for the current weights (needs the complete diagonal).
+ira_status run_pairing(ira_context* h) {
+  ProfScope ps(h, KC_RHS);
+  IRA_CUDA(h, cudaMemsetAsync(h->npairs.p, 0, sizeof(int), h->stream));
+  k_pair_best<<<grid_slices(h), 256, 0, h->stream>>>(h->sell_row.as<int>(), h->slice_off.as<int>(),
+                                                     h->slice_width.as<int>(), h->sell_col.as<int>(),
+                                                     h->sell_w2.as<double>(), h->diag.as<double>(), h->nslices,
+                                                     h->opt.pair_theta, h->pair_key.as<unsigned long long>(),
+                                                     h->pair_w2.as<double>());
+  IRA_TRY(launch_check(h, "k_pair_best"));
+  k_pair_mate<<<grid_nodes(h, h->n), 256, 0, h->stream>>>(h->pair_key.as<unsigned long long>(), h->pair_w2.as<double>(),
+                                                         h->diag.as<double>(), h->n, h->mate.as<int>(),
+                                                         h->pinv.as<double>(), h->npairs.as<int>());
+  return launch_check(h, "k_pair_mate");
+}
+
 ira_status solve_pcg_persistent(ira_context* h) {
   IRA_TRY(run_rhs(h));
+  const bool pairing = h->opt.pair_theta > 0.0;
+  if (pairing) IRA_TRY(run_pairing(h));
   PcgParams pp;
+  pp.mate = pairing ? h->mate.as<int>() : nullptr;
+  pp.pinv = pairing ? h->pinv.as<double>() : nullptr;
+  pp.npairs = pairing ? h->npairs.as<int>() : nullptr;
   pp.n = h->n; pp.nslices = h->nslices; pp.max_iters = std::max(0, h->opt.cg_max_iters);
   pp.rtol2 = h->opt.cg_rtol * h->opt.cg_rtol;
   pp.sell_row = h->sell_row.as<int>(); pp.slice_off = h->slice_off.as<int>(); pp.slice_width = h->slice_width.as<int>();
@@ -439,6 +461,11 @@ ira_status alloc_problem(ira_context* h, int64_t m, int n) {
     IRA_CUDA(h, b->reserve(sizeof(double4) * (size_t)std::max(n, 1)));
   IRA_CUDA(h, h->diag.reserve(sizeof(double) * (size_t)std::max(n, 1)));
   IRA_CUDA(h, h->dinv.reserve(sizeof(double) * (size_t)std::max(n, 1)));
+  IRA_CUDA(h, h->pair_key.reserve(sizeof(unsigned long long) * (size_t)std::max(n, 1)));
+  IRA_CUDA(h, h->pair_w2.reserve(sizeof(double) * (size_t)std::max(n, 1)));
+  IRA_CUDA(h, h->mate.reserve(sizeof(int) * (size_t)std::max(n, 1)));
+  IRA_CUDA(h, h->pinv.reserve(sizeof(double) * (size_t)std::max(n, 1)));
+  IRA_CUDA(h, h->npairs.reserve(sizeof(int)));
   return IRA_OK;
 }
 
@@ -581,6 +608,7 @@ ira_status ira_options_default(ira_options* o) {
   o->device = -1;
   o->cg_max_iters = 20000;
   o->cg_rtol = 1e-10;
+  o->pair_theta = 0.2;
   o->cg_check_every = 16;
   o->lanes_per_row = 0;
   o->world_size = 1;
@@ -630,7 +658,8 @@ ira_status ira_destroy(ira_handle h) {
   for (DevBuf* b : {&h->I, &h->QQ, &h->weights, &h->wres, &h->Q, &h->Q0, &h->stage, &h->rowptr, &h->ent_col,
                     &h->ent_eid, &h->ent_w2, &h->keys, &h->vals, &h->cubtmp, &h->X, &h->R, &h->Z, &h->P,
                     &h->AP, &h->B, &h->diag, &h->dinv, &h->ctl, &h->partials, &h->bad, &h->flush, &h->S, &h->sell_row,
-                    &h->slice_off, &h->slice_width, &h->slice_cnt, &h->sell_col, &h->sell_eid, &h->sell_w2})
+                    &h->slice_off, &h->slice_width, &h->slice_cnt, &h->sell_col, &h->sell_eid, &h->sell_w2,
+                    &h->pair_key, &h->pair_w2, &h->mate, &h->pinv, &h->npairs})
     b->release();
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);

@@ -244,6 +244,73 @@ k_spmv_sell(const int* __restrict__ sell_row, const int* __restrict__ slice_off,
   }
 }
 
+// ---- pairwise block-Jacobi ("mate") preconditioner ----------------------------------------------
+// Robust IRLS weights (L1 above all: weights^2 = 1/|E| up to 1e8) tie a few nodes together with edges
+// 10^3..10^6 times stiffer than the rest; Jacobi then leaves eigenvalues ~ soft/stiff and PCG needs
+// 10^3..10^4 iterations.  Pair every node with its strongest neighbour when the pick is mutual and
+// the normalised strength w2_vu / sqrt(d_v d_u) >= theta, and add the exact coarse correction of
+// the pair's common mode:   M^-1 r = D^-1 r + P (P^T L P)_diag^-1 P^T r,   P^T L P = d_v + d_u - 2 w2_vu.
+// (numpy study, SURVEY-style probe: 5 600 -> 65 iterations at n = 10k after 20 L1 iterations.)
+__global__ void __launch_bounds__(256)
+k_pair_best(const int* __restrict__ sell_row, const int* __restrict__ slice_off, const int* __restrict__ slice_width,
+            const int* __restrict__ sell_col, const double* __restrict__ sell_w2, const double* __restrict__ diag,
+            int nslices, double theta, unsigned long long* __restrict__ pair_key, double* __restrict__ pair_w2) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (int s = blockIdx.x + gridDim.x * warp; s < nslices; s += gridDim.x * wpb) {
+    const int row = sell_row[s * kSellC + lane];
+    if (row < 0) continue;
+    const int width = slice_width[s];
+    const int64_t base = (int64_t)slice_off[s] + lane;
+    const double dr = diag[row];
+    unsigned long long best = 0ull;
+    double bw = 0.0;
+    if (dr > 0.0) {
+      for (int j = 0; j < width; ++j) {
+        const int64_t o = base + (int64_t)j * kSellC;
+        const double w2 = sell_w2[o];
+        const int c = sell_col[o];
+        if (w2 > 0.0 && c != row) {
+          const double dc = diag[c];
+          if (dc > 0.0) {                                   // fixed nodes (diag 0) never pair
+            const float st = (float)(w2 / sqrt(dr * dc));
+            if (st >= (float)theta) {
+              const unsigned long long key = ((unsigned long long)__float_as_uint(st) << 32) | (unsigned long long)(0xffffffffu - (unsigned)c);
+              if (key > best) { best = key; bw = w2; }
+            }
+          }
+        }
+      }
+    }
+    pair_key[row] = best;
+    pair_w2[row] = bw;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_pair_mate(const unsigned long long* __restrict__ pair_key, const double* __restrict__ pair_w2,
+            const double* __restrict__ diag, int n, int* __restrict__ mate, double* __restrict__ pinv, int* __restrict__ npairs) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+    int m = -1;
+    double pi = 0.0;
+    const unsigned long long kv = pair_key[v];
+    if (kv) {
+      const int u = (int)(0xffffffffu - (unsigned)(kv & 0xffffffffull));
+      const unsigned long long ku = pair_key[u];
+      if (ku && (int)(0xffffffffu - (unsigned)(ku & 0xffffffffull)) == v && (ku >> 32) == (kv >> 32)) {
+        const double sum = diag[v] + diag[u];
+        const double dc = sum - 2.0 * pair_w2[v < u ? v : u];   // one value for both members: symmetric M
+        if (dc > 1e-12 * sum) {                            // a floating 2-node component has dc = 0
+          m = u; pi = 1.0 / dc;
+          if (v < u) atomicAdd(npairs, 1);
+        }
+      }
+    }
+    mate[v] = m;
+    pinv[v] = pi;
+  }
+}
+
 // ---- the persistent solve ----------------------------------------------------------------------
 struct PcgParams {
   int n, nslices, max_iters;
@@ -253,6 +320,7 @@ struct PcgParams {
   const double4* B; const double* diag;
   double4 *X, *R, *U, *W, *P, *S;
   double* dinv;
+  const int* mate; const double* pinv; const int* npairs;   // pairwise block-Jacobi (null / 0 pairs: Jacobi)
   double* partials;      // [gridDim.x][kPcgNV]
   Ctl* ctl;
 };
@@ -300,6 +368,7 @@ k_pcg_persistent(const PcgParams p) {
   const int gwarp = blockIdx.x + gridDim.x * (threadIdx.x >> 5);
   const int nwarps = gridDim.x * (blockDim.x >> 5);
   double v[kPcgNV];
+  const bool has_pairs = p.npairs != nullptr && *p.npairs > 0;      // grid-uniform
 
   // ---- start: x = 0, r = b, u = M^-1 r, p = s = 0; |b|^2 ---------------------------------------
 #pragma unroll
@@ -314,7 +383,16 @@ k_pcg_persistent(const PcgParams p) {
       const double4 z4 = make_double4(0, 0, 0, 0);
       st256(p.X + row, z4); st256(p.P + row, z4); st256(p.S + row, z4);
       st256(p.R + row, b);
-      st256(p.U + row, make_double4(di * b.x, di * b.y, di * b.z, 0.0));
+      double4 u0 = make_double4(di * b.x, di * b.y, di * b.z, 0.0);
+      if (has_pairs) {
+        const int mt = p.mate[row];
+        if (mt >= 0) {                                      // B is complete (written by the previous kernel)
+          const double4 bm = ldg256(p.B + mt);
+          const double pi = p.pinv[row];
+          u0.x += pi * (b.x + bm.x); u0.y += pi * (b.y + bm.y); u0.z += pi * (b.z + bm.z);
+        }
+      }
+      st256(p.U + row, u0);
       v[0] += b.x * b.x; v[1] += b.y * b.y; v[2] += b.z * b.z;
     }
   }
@@ -394,11 +472,30 @@ k_pcg_persistent(const PcgParams p) {
         x.x += a0 * pp.x; x.y += a1 * pp.y; x.z += a2 * pp.z;
         r.x -= a0 * ss.x; r.y -= a1 * ss.y; r.z -= a2 * ss.z;
         st256(p.X + row, x); st256(p.R + row, r);
-        st256(p.U + row, make_double4(di * r.x, di * r.y, di * r.z, 0.0));
+        if (!has_pairs) st256(p.U + row, make_double4(di * r.x, di * r.y, di * r.z, 0.0));
       }
     }
     ++it;
-    grid.sync();                                        // new u visible before the next gathers
+    grid.sync();                                        // new u (or new r) visible to the whole grid
+    if (has_pairs) {
+      // u = D^-1 r + pair correction; the mate's r was written by another thread before the barrier
+      for (int s = gwarp; s < p.nslices; s += nwarps) {
+        const int row = p.sell_row[s * kSellC + lane];
+        if (row >= 0) {
+          const double4 r = ld256(p.R + row);
+          const double di = p.dinv[row];
+          double4 u = make_double4(di * r.x, di * r.y, di * r.z, 0.0);
+          const int mt = p.mate[row];
+          if (mt >= 0) {
+            const double4 rm = ld256(p.R + mt);
+            const double pi = p.pinv[row];
+            u.x += pi * (r.x + rm.x); u.y += pi * (r.y + rm.y); u.z += pi * (r.z + rm.z);
+          }
+          st256(p.U + row, u);
+        }
+      }
+      grid.sync();
+    }
     if (timer) { const long long c = clock64(); c_upd += c - c_mark; c_mark = c; }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
