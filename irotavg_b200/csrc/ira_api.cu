@@ -88,11 +88,12 @@ struct ira_context {
   DevBuf X, R, Z, P, AP, B, diag, dinv, S;
   // SELL-32-sigma copy of the pattern (ira_pcg.cuh)
   DevBuf sell_row, slice_off, slice_width, slice_cnt, sell_col, sell_eid, sell_w2;
-  DevBuf pair_key, pair_w2, mate, pinv, npairs;
+  DevBuf pair_key, pair_key2, pair_w2, mate, pc1, pc2, npairs;
   int nslices = 0, npos = 0;
   int64_t sell_total = 0;
   bool fmt_csr = false;      // multi-kernel path on the CSR sub-warp kernels (lanes_per_row set)
   bool persistent = true;    // one cooperative kernel per linear solve
+  bool pairing = false;      // 2x2 block-Jacobi active in the multi-kernel path
   int pcg_blocks_per_sm = 0;
   DevBuf ctl, partials, bad, flush;
   Ctl* h_ctl = nullptr;  // pinned
@@ -305,6 +306,15 @@ ira_status run_spmv(ira_context* h, bool fuse) {
   }
 }
 
+ira_status allreduce(ira_context* h, const void* src, void* dst, size_t count, ncclDataType_t dt, ncclRedOp_t op) {
+  if (h->opt.world_size <= 1) return IRA_OK;
+  if (!h->comm) { h->err = "world_size > 1 but ira_comm_init was not called"; return IRA_ERR_COMM; }
+  ProfScope ps(h, KC_COMM);
+  ncclResult_t r = g_nccl.AllReduce(src, dst, count, dt, op, h->comm, h->stream);
+  if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r); return IRA_ERR_COMM; }
+  return IRA_OK;
+}
+
 ira_status allreduce_f64(ira_context* h, double* buf, size_t count) {
   if (h->opt.world_size <= 1) return IRA_OK;
   if (!h->comm) { h->err = "world_size > 1 but ira_comm_init was not called"; return IRA_ERR_COMM; }
@@ -319,7 +329,8 @@ ira_status run_cg_init(ira_context* h) {
   k_cg_init<<<grid_nodes(h, h->n, kRedThreads), kRedThreads, 0, h->stream>>>(
       h->B.as<double4>(), h->diag.as<double>(), h->dinv.as<double>(), h->X.as<double4>(),
       h->R.as<double4>(), h->Z.as<double4>(), h->P.as<double4>(), h->n, h->ctl.as<Ctl>(),
-      h->partials.as<double>());
+      h->partials.as<double>(), h->pairing ? h->mate.as<int>() : nullptr, h->pairing ? h->pc1.as<double>() : nullptr,
+      h->pairing ? h->pc2.as<double>() : nullptr);
   return launch_check(h, "k_cg_init");
 }
 
@@ -337,8 +348,15 @@ ira_status run_cg_iteration(ira_context* h) {
     ProfScope ps(h, KC_CGVEC);
     k_cg_update<<<grid_nodes(h, h->n, kRedThreads), kRedThreads, 0, h->stream>>>(
         h->X.as<double4>(), h->R.as<double4>(), h->Z.as<double4>(), h->P.as<double4>(),
-        h->AP.as<double4>(), h->dinv.as<double>(), h->n, h->ctl.as<Ctl>(), h->partials.as<double>());
+        h->AP.as<double4>(), h->dinv.as<double>(), h->n, h->ctl.as<Ctl>(), h->partials.as<double>(),
+        h->pairing ? 1 : 0);
     IRA_TRY(launch_check(h, "k_cg_update"));
+    if (h->pairing) {
+      k_cg_precond<<<grid_nodes(h, h->n, kRedThreads), kRedThreads, 0, h->stream>>>(
+          h->R.as<double4>(), h->Z.as<double4>(), h->mate.as<int>(), h->pc1.as<double>(), h->pc2.as<double>(), h->n,
+          h->ctl.as<Ctl>(), h->partials.as<double>());
+      IRA_TRY(launch_check(h, "k_cg_precond"));
+    }
   }
   {
     ProfScope ps(h, KC_CGVEC);
@@ -368,9 +386,18 @@ ira_status run_pairing(ira_context* h) {
                                                      h->opt.pair_theta, h->pair_key.as<unsigned long long>(),
                                                      h->pair_w2.as<double>());
   IRA_TRY(launch_check(h, "k_pair_best"));
+  if (h->opt.world_size > 1) {        // a node's edges live on several ranks: global strongest pick
+    IRA_TRY(allreduce(h, h->pair_key.p, h->pair_key2.p, (size_t)h->n, ncclUint64, ncclMax));
+    k_pair_select<<<grid_nodes(h, h->n), 256, 0, h->stream>>>(h->pair_key.as<unsigned long long>(),
+                                                           h->pair_key2.as<unsigned long long>(), h->pair_w2.as<double>(), h->n);
+    IRA_TRY(launch_check(h, "k_pair_select"));
+    IRA_CUDA(h, cudaMemcpyAsync(h->pair_key.p, h->pair_key2.p, sizeof(unsigned long long) * (size_t)h->n,
+                                cudaMemcpyDeviceToDevice, h->stream));
+    IRA_TRY(allreduce(h, h->pair_w2.p, h->pair_w2.p, (size_t)h->n, ncclFloat64, ncclMax));
+  }
   k_pair_mate<<<grid_nodes(h, h->n), 256, 0, h->stream>>>(h->pair_key.as<unsigned long long>(), h->pair_w2.as<double>(),
                                                          h->diag.as<double>(), h->n, h->mate.as<int>(),
-                                                         h->pinv.as<double>(), h->npairs.as<int>());
+                                                         h->pc1.as<double>(), h->pc2.as<double>(), h->npairs.as<int>());
   return launch_check(h, "k_pair_mate");
 }
 
@@ -380,7 +407,8 @@ ira_status solve_pcg_persistent(ira_context* h) {
   if (pairing) IRA_TRY(run_pairing(h));
   PcgParams pp;
   pp.mate = pairing ? h->mate.as<int>() : nullptr;
-  pp.pinv = pairing ? h->pinv.as<double>() : nullptr;
+  pp.pc1 = pairing ? h->pc1.as<double>() : nullptr;
+  pp.pc2 = pairing ? h->pc2.as<double>() : nullptr;
   pp.npairs = pairing ? h->npairs.as<int>() : nullptr;
   pp.n = h->n; pp.nslices = h->nslices; pp.max_iters = std::max(0, h->opt.cg_max_iters);
   pp.rtol2 = h->opt.cg_rtol * h->opt.cg_rtol;
@@ -412,6 +440,8 @@ ira_status solve_pcg(ira_context* h, int* iters_out, double* relres_out, int* hi
   IRA_TRY(run_rhs(h));
   IRA_TRY(allreduce_f64(h, h->B.as<double>(), (size_t)h->n * 4));
   IRA_TRY(allreduce_f64(h, h->diag.as<double>(), (size_t)h->n));
+  h->pairing = h->opt.pair_theta > 0.0 && !h->fmt_csr;
+  if (h->pairing) IRA_TRY(run_pairing(h));
   IRA_TRY(run_cg_init(h));
   const int cap = std::max(0, h->opt.cg_max_iters);
   const int every = std::max(1, h->opt.cg_check_every);
@@ -463,8 +493,10 @@ ira_status alloc_problem(ira_context* h, int64_t m, int n) {
   IRA_CUDA(h, h->dinv.reserve(sizeof(double) * (size_t)std::max(n, 1)));
   IRA_CUDA(h, h->pair_key.reserve(sizeof(unsigned long long) * (size_t)std::max(n, 1)));
   IRA_CUDA(h, h->pair_w2.reserve(sizeof(double) * (size_t)std::max(n, 1)));
+  IRA_CUDA(h, h->pair_key2.reserve(sizeof(unsigned long long) * (size_t)std::max(n, 1)));
   IRA_CUDA(h, h->mate.reserve(sizeof(int) * (size_t)std::max(n, 1)));
-  IRA_CUDA(h, h->pinv.reserve(sizeof(double) * (size_t)std::max(n, 1)));
+  IRA_CUDA(h, h->pc1.reserve(sizeof(double) * (size_t)std::max(n, 1)));
+  IRA_CUDA(h, h->pc2.reserve(sizeof(double) * (size_t)std::max(n, 1)));
   IRA_CUDA(h, h->npairs.reserve(sizeof(int)));
   return IRA_OK;
 }
@@ -659,7 +691,7 @@ ira_status ira_destroy(ira_handle h) {
                     &h->ent_eid, &h->ent_w2, &h->keys, &h->vals, &h->cubtmp, &h->X, &h->R, &h->Z, &h->P,
                     &h->AP, &h->B, &h->diag, &h->dinv, &h->ctl, &h->partials, &h->bad, &h->flush, &h->S, &h->sell_row,
                     &h->slice_off, &h->slice_width, &h->slice_cnt, &h->sell_col, &h->sell_eid, &h->sell_w2,
-                    &h->pair_key, &h->pair_w2, &h->mate, &h->pinv, &h->npairs})
+                    &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs})
     b->release();
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -890,6 +922,7 @@ static ira_status probe_prepare(ira_handle h) {   // weights = 1, residual from 
   IRA_CUDA(h, cudaMemcpyAsync(h->Q.p, h->Q0.p, sizeof(double4) * h->n, cudaMemcpyDeviceToDevice, h->stream));
   IRA_TRY(run_residual(h, h->Q.as<double4>(), 0));
   IRA_TRY(run_rhs(h));
+  h->pairing = false;
   IRA_TRY(run_cg_init(h));
   IRA_CUDA(h, cudaStreamSynchronize(h->stream));
   return IRA_OK;
@@ -950,7 +983,7 @@ ira_status ira_probe_time_kernel(ira_handle h, int32_t which, int32_t reps, int3
       default:
         k_cg_update<<<grid_nodes(h, h->n, kRedThreads), kRedThreads, 0, h->stream>>>(
             h->X.as<double4>(), h->R.as<double4>(), h->Z.as<double4>(), h->P.as<double4>(), h->AP.as<double4>(),
-            h->dinv.as<double>(), h->n, h->ctl.as<Ctl>(), h->partials.as<double>());
+            h->dinv.as<double>(), h->n, h->ctl.as<Ctl>(), h->partials.as<double>(), 0);
         return launch_check(h, "k_cg_update");
     }
   };

@@ -323,16 +323,25 @@ k_rhs_diag(const int* __restrict__ rowptr, const int* __restrict__ ent_eid, cons
 __global__ void __launch_bounds__(kRedThreads)
 k_cg_init(const double4* __restrict__ B, const double* __restrict__ diag, double* __restrict__ dinv,
           double4* __restrict__ X, double4* __restrict__ R, double4* __restrict__ Z, double4* __restrict__ P,
-          int n, Ctl* ctl, double* partials) {
+          int n, Ctl* ctl, double* partials, const int* __restrict__ mate, const double* __restrict__ pc1,
+          const double* __restrict__ pc2) {
   __shared__ double sm[6 * 32];
   __shared__ int flag;
   double v[6] = {0, 0, 0, 0, 0, 0};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double4 b = ldg256(B + i);
     const double d = diag[i];
-    const double di = d > 0.0 ? 1.0 / d : 0.0;
+    const double di = pc1 ? pc1[i] : (d > 0.0 ? 1.0 / d : 0.0);     // 2x2 block-Jacobi c1, or 1/d
     dinv[i] = di;
-    const double4 z = make_double4(di * b.x, di * b.y, di * b.z, 0.0);
+    double4 z = make_double4(di * b.x, di * b.y, di * b.z, 0.0);
+    if (mate) {
+      const int mt = mate[i];
+      if (mt >= 0) {
+        const double4 bm = ldg256(B + mt);
+        const double c2 = pc2[i];
+        z.x += c2 * bm.x; z.y += c2 * bm.y; z.z += c2 * bm.z;
+      }
+    }
     st256(X + i, make_double4(0, 0, 0, 0));
     st256(R + i, b);
     st256(Z + i, z);
@@ -425,11 +434,25 @@ k_cg_dot_pap(const double4* __restrict__ P, const double4* __restrict__ AP, int 
   }
 }
 
+// End of a PCG iteration (one thread): beta from the new r.z, convergence from |r|^2 (already in ctl).
+__device__ __forceinline__ void cg_finish_iteration(Ctl* ctl, const double* rz_new) {
+  int conv = 1;
+  for (int c = 0; c < 3; ++c) {
+    const double rz_old = ctl->rz[c];
+    ctl->beta[c] = rz_old > 0.0 ? rz_new[c] / rz_old : 0.0;
+    ctl->rz[c] = rz_new[c];
+    if (!(ctl->rnorm2[c] <= ctl->rtol2 * ctl->bnorm2[c])) conv = 0;
+  }
+  const int it = ctl->cg_iters + 1;
+  ctl->cg_iters = it;
+  if (conv || it >= ctl->cg_max_iters) ctl->done = 1;
+}
+
 // x += alpha p; r -= alpha Ap; z = M^-1 r; then rz', |r|^2 -> beta, convergence flag.
 __global__ void __launch_bounds__(kRedThreads)
 k_cg_update(double4* __restrict__ X, double4* __restrict__ R, double4* __restrict__ Z,
             const double4* __restrict__ P, const double4* __restrict__ AP, const double* __restrict__ dinv,
-            int n, Ctl* ctl, double* partials) {
+            int n, Ctl* ctl, double* partials, int defer_z) {
   if (ctl->done) return;
   __shared__ double sm[6 * 32];
   __shared__ int flag;
@@ -449,18 +472,34 @@ k_cg_update(double4* __restrict__ X, double4* __restrict__ R, double4* __restric
     v[3] += r.x * r.x; v[4] += r.y * r.y; v[5] += r.z * r.z;
   }
   if (grid_reduce_last<6>(v, partials, &ctl->ticket, sm, &flag) && threadIdx.x == 0) {
-    int conv = 1;
-    for (int c = 0; c < 3; ++c) {
-      const double rz_old = ctl->rz[c];
-      ctl->beta[c] = rz_old > 0.0 ? v[c] / rz_old : 0.0;
-      ctl->rz[c] = v[c];
-      ctl->rnorm2[c] = v[3 + c];
-      if (!(v[3 + c] <= ctl->rtol2 * ctl->bnorm2[c])) conv = 0;
-    }
-    const int it = ctl->cg_iters + 1;
-    ctl->cg_iters = it;
-    if (conv || it >= ctl->cg_max_iters) ctl->done = 1;
+    for (int c = 0; c < 3; ++c) ctl->rnorm2[c] = v[3 + c];
+    if (!defer_z) cg_finish_iteration(ctl, v);     // else k_cg_precond computes z and r.z
   }
+}
+
+// z = M^-1 r for the 2x2 block-Jacobi preconditioner (z_v = c1_v r_v + c2_v r_mate(v)); r must be
+// complete, hence a kernel of its own after k_cg_update(defer_z = 1).  Then r.z -> beta, convergence.
+__global__ void __launch_bounds__(kRedThreads)
+k_cg_precond(const double4* __restrict__ R, double4* __restrict__ Z, const int* __restrict__ mate,
+             const double* __restrict__ pc1, const double* __restrict__ pc2, int n, Ctl* ctl, double* partials) {
+  if (ctl->done) return;
+  __shared__ double sm[3 * 32];
+  __shared__ int flag;
+  double v[3] = {0, 0, 0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double4 r = ldg256(R + i);
+    const double c1 = pc1[i];
+    double4 z = make_double4(c1 * r.x, c1 * r.y, c1 * r.z, 0.0);
+    const int mt = mate[i];
+    if (mt >= 0) {
+      const double4 rm = ldg256(R + mt);
+      const double c2 = pc2[i];
+      z.x += c2 * rm.x; z.y += c2 * rm.y; z.z += c2 * rm.z;
+    }
+    st256(Z + i, z);
+    v[0] += r.x * z.x; v[1] += r.y * z.y; v[2] += r.z * z.z;
+  }
+  if (grid_reduce_last<3>(v, partials, &ctl->ticket, sm, &flag) && threadIdx.x == 0) cg_finish_iteration(ctl, v);
 }
 
 // p = z + beta p

@@ -248,9 +248,9 @@ k_spmv_sell(const int* __restrict__ sell_row, const int* __restrict__ slice_off,
 // Robust IRLS weights (L1 above all: weights^2 = 1/|E| up to 1e8) tie a few nodes together with edges
 // 10^3..10^6 times stiffer than the rest; Jacobi then leaves eigenvalues ~ soft/stiff and PCG needs
 // 10^3..10^4 iterations.  Pair every node with its strongest neighbour when the pick is mutual and
-// the normalised strength w2_vu / sqrt(d_v d_u) >= theta, and add the exact coarse correction of
-// the pair's common mode:   M^-1 r = D^-1 r + P (P^T L P)_diag^-1 P^T r,   P^T L P = d_v + d_u - 2 w2_vu.
-// (numpy study, SURVEY-style probe: 5 600 -> 65 iterations at n = 10k after 20 L1 iterations.)
+// the normalised strength w2_vu / sqrt(d_v d_u) >= theta, and invert the pair's 2x2 diagonal block
+// exactly (block-Jacobi with blocks of size 1 and 2).
+// (numpy study: 5 600 -> ~65 PCG iterations at n = 10k after 20 L1 iterations.)
 __global__ void __launch_bounds__(256)
 k_pair_best(const int* __restrict__ sell_row, const int* __restrict__ slice_off, const int* __restrict__ slice_width,
             const int* __restrict__ sell_col, const double* __restrict__ sell_w2, const double* __restrict__ diag,
@@ -287,27 +287,44 @@ k_pair_best(const int* __restrict__ sell_row, const int* __restrict__ slice_off,
   }
 }
 
+// Sharded path: after the all-reduce(MAX) of pair_key, a rank keeps its candidate weight only if its
+// local pick is the global one (then all-reduce(MAX) of pair_w2 delivers it to every rank).
+__global__ void k_pair_select(const unsigned long long* __restrict__ key_local, const unsigned long long* __restrict__ key_global,
+                              double* __restrict__ pair_w2, int n) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x)
+    if (key_local[v] != key_global[v]) pair_w2[v] = 0.0;
+}
+
+// Mutual picks become 2x2 diagonal blocks [[d_v, -w], [-w, d_u]] of the block-Jacobi preconditioner;
+// their exact inverse is applied as  z_v = c1_v r_v + c2_v r_mate(v)  with
+//   det = d_v d_u - w^2 = w (a + b) + a b   (a = d_v - w, b = d_u - w: no cancellation for stiff w),
+//   c1_v = d_u / det,  c2_v = w / det.      Unpaired nodes keep Jacobi: c1 = 1/d (0 if d = 0), c2 = 0.
 __global__ void __launch_bounds__(256)
 k_pair_mate(const unsigned long long* __restrict__ pair_key, const double* __restrict__ pair_w2,
-            const double* __restrict__ diag, int n, int* __restrict__ mate, double* __restrict__ pinv, int* __restrict__ npairs) {
+            const double* __restrict__ diag, int n, int* __restrict__ mate, double* __restrict__ pc1,
+            double* __restrict__ pc2, int* __restrict__ npairs) {
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
     int m = -1;
-    double pi = 0.0;
+    const double dv = diag[v];
+    double c1 = dv > 0.0 ? 1.0 / dv : 0.0, c2 = 0.0;
     const unsigned long long kv = pair_key[v];
     if (kv) {
       const int u = (int)(0xffffffffu - (unsigned)(kv & 0xffffffffull));
       const unsigned long long ku = pair_key[u];
       if (ku && (int)(0xffffffffu - (unsigned)(ku & 0xffffffffull)) == v && (ku >> 32) == (kv >> 32)) {
-        const double sum = diag[v] + diag[u];
-        const double dc = sum - 2.0 * pair_w2[v < u ? v : u];   // one value for both members: symmetric M
-        if (dc > 1e-12 * sum) {                            // a floating 2-node component has dc = 0
-          m = u; pi = 1.0 / dc;
+        const double du = diag[u];
+        const double w = pair_w2[v < u ? v : u];            // one value for both members: symmetric M
+        const double a = dv - w, b = du - w;
+        const double det = w * (a + b) + a * b;
+        if (a >= 0.0 && b >= 0.0 && det > 1e-12 * dv * du) { // a floating 2-node component has det = 0
+          m = u; c1 = du / det; c2 = w / det;
           if (v < u) atomicAdd(npairs, 1);
         }
       }
     }
     mate[v] = m;
-    pinv[v] = pi;
+    pc1[v] = c1;
+    pc2[v] = c2;
   }
 }
 
@@ -320,7 +337,7 @@ struct PcgParams {
   const double4* B; const double* diag;
   double4 *X, *R, *U, *W, *P, *S;
   double* dinv;
-  const int* mate; const double* pinv; const int* npairs;   // pairwise block-Jacobi (null / 0 pairs: Jacobi)
+  const int* mate; const double* pc1; const double* pc2; const int* npairs;   // 2x2 block-Jacobi (null: Jacobi)
   double* partials;      // [gridDim.x][kPcgNV]
   Ctl* ctl;
 };
@@ -378,7 +395,7 @@ k_pcg_persistent(const PcgParams p) {
     if (row >= 0) {
       const double4 b = ldg256(p.B + row);
       const double d = p.diag[row];
-      const double di = d > 0.0 ? 1.0 / d : 0.0;
+      const double di = p.pc1 ? p.pc1[row] : (d > 0.0 ? 1.0 / d : 0.0);   // c1 of the 2x2 block, or 1/d
       p.dinv[row] = di;
       const double4 z4 = make_double4(0, 0, 0, 0);
       st256(p.X + row, z4); st256(p.P + row, z4); st256(p.S + row, z4);
@@ -388,8 +405,8 @@ k_pcg_persistent(const PcgParams p) {
         const int mt = p.mate[row];
         if (mt >= 0) {                                      // B is complete (written by the previous kernel)
           const double4 bm = ldg256(p.B + mt);
-          const double pi = p.pinv[row];
-          u0.x += pi * (b.x + bm.x); u0.y += pi * (b.y + bm.y); u0.z += pi * (b.z + bm.z);
+          const double c2 = p.pc2[row];
+          u0.x += c2 * bm.x; u0.y += c2 * bm.y; u0.z += c2 * bm.z;
         }
       }
       st256(p.U + row, u0);
@@ -488,8 +505,8 @@ k_pcg_persistent(const PcgParams p) {
           const int mt = p.mate[row];
           if (mt >= 0) {
             const double4 rm = ld256(p.R + mt);
-            const double pi = p.pinv[row];
-            u.x += pi * (r.x + rm.x); u.y += pi * (r.y + rm.y); u.z += pi * (r.z + rm.z);
+            const double c2 = p.pc2[row];
+            u.x += c2 * rm.x; u.y += c2 * rm.y; u.z += c2 * rm.z;
           }
           st256(p.U + row, u);
         }
