@@ -67,7 +67,9 @@ typedef struct ira_options {
   int32_t rank;
   int32_t profile;         /* 1: record CUDA-event timings per kernel class into ira_stats        */
   int32_t solver;          /* PCG driver: 0 = auto (persistent cooperative kernel on one GPU), 1 = one
-                              kernel per CG step with host-polled convergence, 2 = persistent       */
+                              kernel per CG step with host-polled convergence, 2 = persistent;
+                              +4 = persistent kernel keeps its vectors in HBM even when one row per
+                              lane would let them live in registers (A/B measurement)               */
   int32_t spmv_variant;    /* experiment knob: gather flavour / unroll of the SELL SpMV (0 = default)  */
   int32_t reserved[5];
 } ira_options;

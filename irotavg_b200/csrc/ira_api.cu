@@ -85,7 +85,7 @@ struct ira_context {
 
   DevBuf I, QQ, weights, wres, Q, Q0, stage;
   DevBuf rowptr, ent_col, ent_eid, ent_w2, keys, vals, cubtmp;
-  DevBuf X, R, Z, P, AP, B, diag, dinv, S;
+  DevBuf X, R, Z, P, AP, B, diag, dinv, S, R2, S2;
   // SELL-32-sigma copy of the pattern (ira_pcg.cuh)
   DevBuf sell_row, slice_off, slice_width, slice_cnt, sell_col, sell_eid, sell_w2;
   DevBuf pair_key, pair_key2, pair_w2, mate, pc1, pc2, npairs;
@@ -421,9 +421,24 @@ ira_status solve_pcg_persistent(ira_context* h) {
   // one block per SM (slices are dealt round-robin over blocks); tiny graphs use fewer blocks so that
   // the grid barrier has fewer participants
   const int grid = std::max(1, std::min(h->nslices, h->sms * h->pcg_blocks_per_sm));
-  void* args[] = {(void*)&pp};
   ProfScope ps(h, KC_PCG);
   void* fn = nullptr;
+  if (h->nslices <= grid * (kPcgThreads / 32) && !(h->opt.solver & 4)) {   // one row per lane: state in registers
+    PcgRegParams pr;
+    pr.base = pp;
+    pr.RS0r = h->R.as<double4>(); pr.RS0s = h->S.as<double4>(); pr.RS1r = h->R2.as<double4>(); pr.RS1s = h->S2.as<double4>();
+    void* rargs[] = {(void*)&pr};
+    switch (h->opt.spmv_variant) {
+      case 1: fn = (void*)k_pcg_persistent_reg<1, 4>; break;
+      case 3: fn = (void*)k_pcg_persistent_reg<0, 8>; break;
+      case 4: fn = (void*)k_pcg_persistent_reg<1, 8>; break;
+      default: fn = (void*)k_pcg_persistent_reg<0, 4>; break;
+    }
+    IRA_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPcgThreads), rargs, 0, h->stream));
+    h->launches++;
+    return IRA_OK;
+  }
+  void* args[] = {(void*)&pp};
   switch (h->opt.spmv_variant) {
     case 1: fn = (void*)k_pcg_persistent<1, 4>; break;
     case 3: fn = (void*)k_pcg_persistent<0, 8>; break;
@@ -487,7 +502,7 @@ ira_status alloc_problem(ira_context* h, int64_t m, int n) {
   IRA_CUDA(h, h->ent_w2.reserve(sizeof(double) * (size_t)std::max<int64_t>(2 * m, 1)));
   IRA_CUDA(h, h->keys.reserve(sizeof(int) * (size_t)std::max<int64_t>(4 * m, 1)));
   IRA_CUDA(h, h->vals.reserve(sizeof(int) * (size_t)std::max<int64_t>(4 * m, 1)));
-  for (DevBuf* b : {&h->X, &h->R, &h->Z, &h->P, &h->AP, &h->B, &h->S})
+  for (DevBuf* b : {&h->X, &h->R, &h->Z, &h->P, &h->AP, &h->B, &h->S, &h->R2, &h->S2})
     IRA_CUDA(h, b->reserve(sizeof(double4) * (size_t)std::max(n, 1)));
   IRA_CUDA(h, h->diag.reserve(sizeof(double) * (size_t)std::max(n, 1)));
   IRA_CUDA(h, h->dinv.reserve(sizeof(double) * (size_t)std::max(n, 1)));
@@ -691,7 +706,7 @@ ira_status ira_destroy(ira_handle h) {
                     &h->ent_eid, &h->ent_w2, &h->keys, &h->vals, &h->cubtmp, &h->X, &h->R, &h->Z, &h->P,
                     &h->AP, &h->B, &h->diag, &h->dinv, &h->ctl, &h->partials, &h->bad, &h->flush, &h->S, &h->sell_row,
                     &h->slice_off, &h->slice_width, &h->slice_cnt, &h->sell_col, &h->sell_eid, &h->sell_w2,
-                    &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs})
+                    &h->R2, &h->S2, &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs})
     b->release();
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -724,7 +739,7 @@ ira_status ira_problem_upload(ira_handle h, int64_t m, int64_t n_total, int32_t 
     IRA_TRY(build_sell(h));
     if (h->sell_total > 3ll * std::max(h->nnz, 1) + 64ll * kSellSigma) h->fmt_csr = true;
   }
-  h->persistent = !h->fmt_csr && h->opt.world_size <= 1 && h->opt.solver != 1 && h->pcg_blocks_per_sm > 0;
+  h->persistent = !h->fmt_csr && h->opt.world_size <= 1 && (h->opt.solver & 3) != 1 && h->pcg_blocks_per_sm > 0;
   h->prev_cg = 0;
   h->uploaded = true;
   return IRA_OK;

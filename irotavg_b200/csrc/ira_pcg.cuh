@@ -529,4 +529,150 @@ k_pcg_persistent(const PcgParams p) {
   }
 }
 
+// ---- register-resident variant -----------------------------------------------------------------------
+// When the graph has no more slices than the grid has warps (n <= 148 x 24 x 32 = 113 664 rows, i.e.
+// config 3), every lane owns exactly one row for the whole solve and keeps its x, r, p, s (and the
+// preconditioner coefficients) in registers: per iteration only u is written (32 B / row) and gathered;
+// the 350 B / row of vector streams of the general kernel disappear, and so does its third barrier:
+// a paired row recomputes its mate's new residual from the mate's (r, s) of the PREVIOUS iteration
+// (ping-pong buffers RS[it & 1], written only by paired rows) and the mate's w of this iteration, all
+// of which were published before the reduction barrier.
+struct PcgRegParams {
+  PcgParams base;
+  double4* RS0r; double4* RS0s; double4* RS1r; double4* RS1s;   // ping-pong (r, s) of paired rows
+};
+
+template <int V, int UNR>
+__global__ void __launch_bounds__(kPcgThreads, 1)
+k_pcg_persistent_reg(const PcgRegParams q) {
+  const PcgParams& p = q.base;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double red[kPcgNV * 32];
+  __shared__ double tot[kPcgNV];
+  __shared__ double sc_bb[3], sc_go[3], sc_ao[3], sc_a[3], sc_b[3], sc_rr[3];
+  __shared__ int sc_stop;
+  const int lane = threadIdx.x & 31;
+  const int slice = blockIdx.x + gridDim.x * (threadIdx.x >> 5);     // <= 1 slice per warp
+  const bool has_pairs = p.npairs != nullptr && *p.npairs > 0;
+  int row = -1, width = 0, mt = -1;
+  int64_t base = 0;
+  if (slice < p.nslices) {
+    row = p.sell_row[slice * kSellC + lane];
+    width = p.slice_width[slice];
+    base = (int64_t)p.slice_off[slice] + lane;
+  }
+  double v[kPcgNV];
+#pragma unroll
+  for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
+  double x0 = 0, x1 = 0, x2 = 0, r0 = 0, r1 = 0, r2 = 0, p0 = 0, p1 = 0, p2 = 0, s0 = 0, s1 = 0, s2 = 0;
+  double u0 = 0, u1 = 0, u2 = 0, di = 0, c2 = 0;
+  if (row >= 0) {
+    const double4 b = ldg256(p.B + row);
+    const double d = p.diag[row];
+    di = p.pc1 ? p.pc1[row] : (d > 0.0 ? 1.0 / d : 0.0);
+    r0 = b.x; r1 = b.y; r2 = b.z;
+    u0 = di * r0; u1 = di * r1; u2 = di * r2;
+    if (has_pairs) {
+      mt = p.mate[row];
+      if (mt >= 0) {
+        c2 = p.pc2[row];
+        const double4 bm = ldg256(p.B + mt);
+        u0 += c2 * bm.x; u1 += c2 * bm.y; u2 += c2 * bm.z;
+        st256(q.RS1r + row, b);                                      // "previous" buffer of iteration 0
+        st256(q.RS1s + row, make_double4(0, 0, 0, 0));
+      }
+    }
+    st256(p.U + row, make_double4(u0, u1, u2, 0.0));
+    v[0] = r0 * r0; v[1] = r1 * r1; v[2] = r2 * r2;
+  }
+  pcg_grid_reduce(v, p.partials, grid, red, tot);
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < 3; ++c) { sc_bb[c] = v[c]; sc_rr[c] = v[c]; sc_go[c] = 1.0; sc_ao[c] = 1.0; }
+    sc_stop = !(v[0] > 0.0 || v[1] > 0.0 || v[2] > 0.0);
+  }
+  __syncthreads();
+  int it = 0;
+  const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+  long long c_spmv = 0, c_upd = 0, c_mark = 0, c_begin = 0;
+  unsigned long long ns_begin = 0;
+  if (timer) { c_begin = c_mark = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_begin)); }
+
+  while (!sc_stop) {
+    double w0 = 0, w1 = 0, w2 = 0;
+    if (row >= 0 || width > 0) {
+      sell_row_apply<V, UNR>(p.sell_col, p.sell_w2, p.U, base, width, make_double4(u0, u1, u2, 0.0), w0, w1, w2);
+    }
+    if (row >= 0) {
+      if (mt >= 0) st256(p.W + row, make_double4(w0, w1, w2, 0.0));   // the mate needs it after the barrier
+      v[0] = r0 * u0; v[1] = r1 * u1; v[2] = r2 * u2;
+      v[3] = u0 * w0; v[4] = u1 * w1; v[5] = u2 * w2;
+      v[6] = r0 * r0; v[7] = r1 * r1; v[8] = r2 * r2;
+    } else {
+#pragma unroll
+      for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
+    }
+    pcg_grid_reduce(v, p.partials, grid, red, tot);
+    if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; }
+    if (threadIdx.x == 0) {
+      bool conv = true;
+      for (int c = 0; c < 3; ++c) {
+        sc_rr[c] = v[6 + c];
+        if (!(v[6 + c] <= p.rtol2 * sc_bb[c])) conv = false;
+      }
+      if (conv || it >= p.max_iters) {
+        sc_stop = 1;
+      } else {
+        for (int c = 0; c < 3; ++c) {
+          const double gam = v[c], del = v[3 + c];
+          double beta = 0.0, den = del;
+          if (it > 0) {
+            beta = sc_go[c] > 0.0 ? gam / sc_go[c] : 0.0;
+            if (sc_ao[c] != 0.0) den = del - beta * gam / sc_ao[c];
+          }
+          const double alpha = den > 0.0 ? gam / den : 0.0;
+          sc_go[c] = gam; sc_ao[c] = alpha; sc_a[c] = alpha; sc_b[c] = beta;
+        }
+      }
+    }
+    __syncthreads();
+    if (sc_stop) break;
+    const double a0 = sc_a[0], a1 = sc_a[1], a2 = sc_a[2], b0 = sc_b[0], b1 = sc_b[1], b2 = sc_b[2];
+    if (row >= 0) {
+      p0 = u0 + b0 * p0; p1 = u1 + b1 * p1; p2 = u2 + b2 * p2;
+      s0 = w0 + b0 * s0; s1 = w1 + b1 * s1; s2 = w2 + b2 * s2;
+      x0 += a0 * p0; x1 += a1 * p1; x2 += a2 * p2;
+      r0 -= a0 * s0; r1 -= a1 * s1; r2 -= a2 * s2;
+      u0 = di * r0; u1 = di * r1; u2 = di * r2;
+      if (mt >= 0) {
+        double4* const curR = (it & 1) ? q.RS1r : q.RS0r;
+        double4* const curS = (it & 1) ? q.RS1s : q.RS0s;
+        const double4* const oldR = (it & 1) ? q.RS0r : q.RS1r;
+        const double4* const oldS = (it & 1) ? q.RS0s : q.RS1s;
+        const double4 rm = ld256(oldR + mt), sm = ld256(oldS + mt), wm = ld256(p.W + mt);
+        const double sm0 = wm.x + b0 * sm.x, sm1 = wm.y + b1 * sm.y, sm2 = wm.z + b2 * sm.z;   // the mate's new s
+        u0 += c2 * (rm.x - a0 * sm0); u1 += c2 * (rm.y - a1 * sm1); u2 += c2 * (rm.z - a2 * sm2);
+        st256(curR + row, make_double4(r0, r1, r2, 0.0));
+        st256(curS + row, make_double4(s0, s1, s2, 0.0));
+      }
+      st256(p.U + row, make_double4(u0, u1, u2, 0.0));
+    }
+    ++it;
+    grid.sync();
+    if (timer) { const long long c = clock64(); c_upd += c - c_mark; c_mark = c; }
+  }
+  if (row >= 0) st256(p.X + row, make_double4(x0, x1, x2, 0.0));
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    p.ctl->cg_iters = it;
+    for (int c = 0; c < 3; ++c) { p.ctl->bnorm2[c] = sc_bb[c]; p.ctl->rnorm2[c] = sc_rr[c]; }
+    p.ctl->done = 1;
+    unsigned long long ns_end;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_end));
+    p.ctl->cyc_spmv += c_spmv;
+    p.ctl->cyc_update += c_upd;
+    p.ctl->cyc_total += clock64() - c_begin;
+    p.ctl->ns_total += (long long)(ns_end - ns_begin);
+    p.ctl->pcg_spmv_phases += c_spmv > 0 ? it + 1 : 0;
+  }
+}
+
 }  // namespace ira
