@@ -135,6 +135,23 @@ ira_status ira_irls_resident(ira_handle h, int32_t cost, double sigma, int32_t m
                              ira_stats* stats);
 ira_status ira_problem_download(ira_handle h, double* Q, int64_t ld_q, double* weights);
 
+/* ---- irotavg::l1ra  (ral/l1_irls.hpp:98-101, ral/l1_irls.cpp:851-912) -------------------------
+ * The L1RA initial stage both callers run before irls (ral/test.cpp:295, src/ViewGraph.cpp:1407):
+ * per outer iteration three primal-dual interior-point L1 regressions (l1decode_pd, ral/l1_irls.cpp:
+ * 228-468, two Newton steps each), whose Newton systems A'^T diag(sigx) A' dx = w1p (UMFPACK LU in the
+ * reference) are solved by the persistent PCG kernel.  Q rows [f, n_total) are updated in place;
+ * *iters_out / *runtime_s_out are the reference's `iter` / `runtime`.  stats->score[] holds the outer
+ * scores, stats->cg_iters[] the Newton-PCG iterations per outer iteration.  Single GPU. */
+ira_status ira_l1ra(ira_handle h, int64_t m, int64_t n_total, int32_t f,
+                    const int32_t* I_pairs, const double* QQ, int64_t ld_qq,
+                    double* Q, int64_t ld_q, int32_t max_iters, double change_th,
+                    int32_t* iters_out, double* runtime_s_out, ira_stats* stats /* may be NULL */);
+ira_status ira_l1ra_resident(ira_handle h, int32_t max_iters, double change_th,
+                             int32_t* iters_out, double* runtime_s_out, ira_stats* stats);
+/* mode 0 (default after an upload): ira_*_resident calls restart from the uploaded Q0;
+ * mode 1: they continue from the current device Q (l1ra followed by irls, like both callers). */
+ira_status ira_resident_start(ira_handle h, int32_t mode);
+
 /* ---- irotavg::make_A  (ral/l1_irls.hpp:92, ral/l1_irls.cpp:755-780) -------------------------
  * Host helper (no device): writes per edge the two column indices of row k of A, or -1:
  * col_plus[k] = j-f if j >= f else -1;  col_minus[k] = i-f if (j >= f and i >= f) else -1. */

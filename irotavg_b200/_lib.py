@@ -20,6 +20,7 @@ SYMBOLS = [
     "ira_abi_version", "ira_device_count", "ira_get_stream", "ira_irls", "ira_problem_upload", "ira_irls_resident",
     "ira_problem_download", "ira_make_A", "ira_quat_normalised", "ira_probe_residual",
     "ira_probe_laplacian_apply", "ira_probe_time_kernel", "ira_comm_unique_id", "ira_comm_init",
+    "ira_l1ra", "ira_l1ra_resident", "ira_resident_start",
 ]
 
 
@@ -107,6 +108,9 @@ def load():
         "ira_probe_time_kernel": (i32, [H, i32, i32, i32, pf64]),
         "ira_comm_unique_id": (i32, [pu8]),
         "ira_comm_init": (i32, [H, pu8]),
+        "ira_l1ra": (i32, [H, i64, i64, i32, pi32, pf64, i64, pf64, i64, i32, f64, pi32, pf64, C.POINTER(Stats)]),
+        "ira_l1ra_resident": (i32, [H, i32, f64, pi32, pf64, C.POINTER(Stats)]),
+        "ira_resident_start": (i32, [H, i32]),
     }
     for name, (res, args) in sig.items():
         if not hasattr(lib, name):

@@ -177,6 +177,33 @@ class Solver:
                                        C.byref(st)), self._h)
         return np.ascontiguousarray(Qf), weights, _info(st, iters.value, runtime.value)
 
+    # -- irotavg::l1ra ------------------------------------------------------------------------
+    def l1ra(self, QQ, I, A, Q, f, max_iters, change_th):
+        """irotavg::l1ra (ral/l1_irls.hpp:98-101).  Returns (Q_new, info); Q is not modified."""
+        QQf = _colmajor(QQ, 4)
+        Qf = np.array(_colmajor(Q, 4), order="F", copy=True)
+        Ip = _pairs(I)
+        m, n = QQf.shape[0], Qf.shape[0]
+        iters = C.c_int32(0)
+        runtime = C.c_double(0.0)
+        st = Stats()
+        self._check(self._lib.ira_l1ra(self._h, m, n, int(f), _pi(Ip), _pd(QQf), max(m, 1), _pd(Qf), max(n, 1),
+                                       int(max_iters), float(change_th), C.byref(iters), C.byref(runtime),
+                                       C.byref(st)), self._h)
+        return np.ascontiguousarray(Qf), _info(st, iters.value, runtime.value)
+
+    def l1ra_resident(self, max_iters, change_th) -> IrlsInfo:
+        iters = C.c_int32(0)
+        runtime = C.c_double(0.0)
+        st = Stats()
+        self._check(self._lib.ira_l1ra_resident(self._h, int(max_iters), float(change_th), C.byref(iters),
+                                                C.byref(runtime), C.byref(st)), self._h)
+        return _info(st, iters.value, runtime.value)
+
+    def resident_start(self, from_current: bool):
+        """False: resident calls restart from the uploaded Q0; True: continue from the current device Q."""
+        self._check(self._lib.ira_resident_start(self._h, 1 if from_current else 0), self._h)
+
     # -- device-resident variant --------------------------------------------------------------
     def upload(self, QQ, I, Q0, f):
         QQf = _colmajor(QQ, 4)
@@ -256,6 +283,12 @@ def irls(QQ, I, A, cost, sigma, Q, f, max_iters, change_th):
     """irotavg::irls.  Returns (Q, weights, iters, runtime) - the reference's in/out parameters."""
     Qn, w, info = _solver().irls(QQ, I, A, cost, sigma, Q, f, max_iters, change_th)
     return Qn, w, info.iters, info.runtime
+
+
+def l1ra(QQ, I, A, Q, f, max_iters, change_th):
+    """irotavg::l1ra.  Returns (Q, iter, runtime)."""
+    Qn, info = _solver().l1ra(QQ, I, A, Q, f, max_iters, change_th)
+    return Qn, info.iters, info.runtime
 
 
 def make_A(n, f, I):

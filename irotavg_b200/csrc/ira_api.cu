@@ -22,6 +22,7 @@
 
 #include "ira_kernels.cuh"
 #include "ira_pcg.cuh"
+#include "ira_l1ra.cuh"
 
 using namespace ira;
 
@@ -89,6 +90,11 @@ struct ira_context {
   // SELL-32-sigma copy of the pattern (ira_pcg.cuh)
   DevBuf sell_row, slice_off, slice_width, slice_cnt, sell_col, sell_eid, sell_w2;
   DevBuf pair_key, pair_key2, pair_w2, mate, pc1, pc2, npairs;
+  // l1ra (ira_l1ra.cuh): per-edge / per-node primal-dual state, allocated on first use
+  DevBuf pdU, pdAX, pdL1, pdL2, pdADX, pdDU, pdDL1, pdDL2, pdEV, pdSIGX, sell_w3;
+  DevBuf pdX, pdATV, pdATDV, pdW1P, pdDX, diag3, dinv3, pdctl, pdtrial;
+  PdCtl* h_pdctl = nullptr;  // pinned
+  int start_mode = 0;        // 0: resident calls restart from the uploaded Q0, 1: continue from the current Q
   int nslices = 0, npos = 0;
   int64_t sell_total = 0;
   bool fmt_csr = false;      // multi-kernel path on the CSR sub-warp kernels (lanes_per_row set)
@@ -539,7 +545,7 @@ ira_status build_csr(ira_context* h) {
     h->launches += 4;
   }
   k_csr_finalize<<<std::max(1, std::min(cdiv(2 * m + 1, 256), h->sms * 16)), 256, 0, h->stream>>>(
-      keys_out, vals_out, h->I.as<int2>(), 2 * m, n, h->rowptr.as<int>(), h->ent_col.as<int>(),
+      keys_out, vals_out, h->I.as<int2>(), 2 * m, n, h->f, h->rowptr.as<int>(), h->ent_col.as<int>(),
       h->ent_eid.as<int>());
   IRA_TRY(launch_check(h, "k_csr_finalize"));
   int host[2] = {0, 0};
@@ -706,10 +712,13 @@ ira_status ira_destroy(ira_handle h) {
                     &h->ent_eid, &h->ent_w2, &h->keys, &h->vals, &h->cubtmp, &h->X, &h->R, &h->Z, &h->P,
                     &h->AP, &h->B, &h->diag, &h->dinv, &h->ctl, &h->partials, &h->bad, &h->flush, &h->S, &h->sell_row,
                     &h->slice_off, &h->slice_width, &h->slice_cnt, &h->sell_col, &h->sell_eid, &h->sell_w2,
-                    &h->R2, &h->S2, &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs})
+                    &h->R2, &h->S2, &h->pdU, &h->pdAX, &h->pdL1, &h->pdL2, &h->pdADX, &h->pdDU, &h->pdDL1, &h->pdDL2, &h->pdEV,
+                    &h->pdSIGX, &h->sell_w3, &h->pdX, &h->pdATV, &h->pdATDV, &h->pdW1P, &h->pdDX, &h->diag3, &h->dinv3,
+                    &h->pdctl, &h->pdtrial, &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs})
     b->release();
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->h_pdctl) cudaFreeHost(h->h_pdctl);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return IRA_OK;
@@ -742,6 +751,9 @@ ira_status ira_problem_upload(ira_handle h, int64_t m, int64_t n_total, int32_t 
   h->persistent = !h->fmt_csr && h->opt.world_size <= 1 && (h->opt.solver & 3) != 1 && h->pcg_blocks_per_sm > 0;
   h->prev_cg = 0;
   h->uploaded = true;
+  h->start_mode = 0;
+  if (h->n > 0) IRA_CUDA(h, cudaMemcpyAsync(h->Q.p, h->Q0.p, sizeof(double4) * h->n, cudaMemcpyDeviceToDevice, h->stream));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));
   return IRA_OK;
 }
 
@@ -765,7 +777,8 @@ ira_status ira_irls_resident(ira_handle h, int32_t cost, double sigma, int32_t m
 
   const int n = h->n;
   const int64_t m = h->m;
-  if (n > 0) IRA_CUDA(h, cudaMemcpyAsync(h->Q.p, h->Q0.p, sizeof(double4) * n, cudaMemcpyDeviceToDevice, h->stream));
+  if (n > 0 && h->start_mode == 0)
+    IRA_CUDA(h, cudaMemcpyAsync(h->Q.p, h->Q0.p, sizeof(double4) * n, cudaMemcpyDeviceToDevice, h->stream));
   k_fill_f64<<<std::max(1, std::min(cdiv(h->m_pad, 256), h->sms * 8)), 256, 0, h->stream>>>(
       h->weights.as<double>(), 1.0, h->m_pad);                          // weights.setOnes() (:577)
   IRA_TRY(launch_check(h, "k_fill_f64"));
@@ -1056,6 +1069,199 @@ ira_status ira_comm_init(ira_handle h, const uint8_t id_in[128]) {
   ncclResult_t r = g_nccl.CommInitRank(&h->comm, h->opt.world_size, id, h->opt.rank);
   if (r != ncclSuccess) { h->err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); return IRA_ERR_COMM; }
   return IRA_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// irotavg::l1ra  (ral/l1_irls.hpp:98-101, ral/l1_irls.cpp:851-912) on the device, ira_l1ra.cuh
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+ira_status l1ra_alloc(ira_context* h) {
+  const size_t e = sizeof(double4) * (size_t)h->m_pad, nn = sizeof(double4) * (size_t)std::max(h->n, 1);
+  for (DevBuf* b : {&h->pdU, &h->pdAX, &h->pdL1, &h->pdL2, &h->pdADX, &h->pdDU, &h->pdDL1, &h->pdDL2, &h->pdEV, &h->pdSIGX})
+    IRA_CUDA(h, b->reserve(e));
+  for (DevBuf* b : {&h->pdX, &h->pdATV, &h->pdATDV, &h->pdW1P, &h->pdDX, &h->diag3, &h->dinv3})
+    IRA_CUDA(h, b->reserve(nn));
+  IRA_CUDA(h, h->sell_w3.reserve(sizeof(double4) * (size_t)std::max<int64_t>(h->sell_total, 1)));
+  IRA_CUDA(h, h->pdctl.reserve(sizeof(PdCtl)));
+  IRA_CUDA(h, h->pdtrial.reserve(sizeof(double) * 8));
+  if (!h->h_pdctl) IRA_CUDA(h, cudaMallocHost((void**)&h->h_pdctl, sizeof(PdCtl)));
+  return IRA_OK;
+}
+
+ira_status fetch_pdctl(ira_context* h) {
+  IRA_CUDA(h, cudaMemcpyAsync(h->h_pdctl, h->pdctl.p, sizeof(PdCtl), cudaMemcpyDeviceToHost, h->stream));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IRA_OK;
+}
+
+int grid_edges(const ira_context* h) { return std::max(1, std::min(cdiv(std::max<int64_t>(h->m, 1), 256), h->sms * 8)); }
+
+ira_status pd_At(ira_context* h, DevBuf& out, int want_norm) {
+  k_pd_At<<<grid_slices(h), 256, 0, h->stream>>>(h->sell_row.as<int>(), h->slice_off.as<int>(), h->slice_width.as<int>(),
+                                                 h->sell_eid.as<int>(), h->pdEV.as<double4>(), out.as<double4>(), h->nslices,
+                                                 want_norm, h->pdctl.as<PdCtl>(), h->partials.as<double>());
+  return launch_check(h, "k_pd_At");
+}
+
+// One call of l1decode_pd for the three coordinates (pdmaxiter Newton steps); result in pdX.
+ira_status l1decode_pd_device(ira_context* h, int pdmaxiter, int* newton_cg_iters, int* hit_max) {
+  const int64_t m = h->m;
+  const int n = h->n;
+  const double4* Y = h->wres.as<double4>();
+  PdCtl* ctl = h->pdctl.as<PdCtl>();
+  double* part = h->partials.as<double>();
+  PdCtl init;
+  memset(&init, 0, sizeof init);
+  init.m2 = 2.0 * (double)m;
+  *h->h_pdctl = init;
+  IRA_CUDA(h, cudaMemcpyAsync(h->pdctl.p, h->h_pdctl, sizeof(PdCtl), cudaMemcpyHostToDevice, h->stream));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));                      // h_pdctl is reused below
+  IRA_CUDA(h, cudaMemsetAsync(h->pdX.p, 0, sizeof(double4) * (size_t)std::max(n, 1), h->stream));
+  const int ge = grid_edges(h);
+  k_pd_absmax<<<ge, 256, 0, h->stream>>>(Y, m, ctl, part);
+  IRA_TRY(launch_check(h, "k_pd_absmax"));
+  k_pd_init<<<ge, 256, 0, h->stream>>>(Y, h->pdU.as<double4>(), h->pdAX.as<double4>(), h->pdL1.as<double4>(),
+                                       h->pdL2.as<double4>(), h->pdEV.as<double4>(), m, ctl, part);
+  IRA_TRY(launch_check(h, "k_pd_init"));
+  IRA_TRY(pd_At(h, h->pdATV, 1));
+  k_pd_rcent<<<ge, 256, 0, h->stream>>>(Y, h->pdU.as<double4>(), h->pdAX.as<double4>(), h->pdL1.as<double4>(),
+                                        h->pdL2.as<double4>(), m, 0, pdmaxiter, ctl, part);
+  IRA_TRY(launch_check(h, "k_pd_rcent"));
+  for (int pd = 0; pd < pdmaxiter; ++pd) {
+    k_pd_prep<<<ge, 256, 0, h->stream>>>(Y, h->pdU.as<double4>(), h->pdAX.as<double4>(), h->pdL1.as<double4>(),
+                                         h->pdL2.as<double4>(), h->pdSIGX.as<double4>(), h->pdEV.as<double4>(), m, ctl);
+    IRA_TRY(launch_check(h, "k_pd_prep"));
+    IRA_TRY(pd_At(h, h->pdW1P, 0));
+    k_sell_hweights<<<grid_slices(h), 256, 0, h->stream>>>(h->sell_row.as<int>(), h->slice_off.as<int>(),
+                                                           h->slice_width.as<int>(), h->sell_eid.as<int>(),
+                                                           h->pdSIGX.as<double4>(), h->sell_w3.as<double4>(),
+                                                           h->diag3.as<double4>(), h->nslices);
+    IRA_TRY(launch_check(h, "k_sell_hweights"));
+    {                                                                 // H dx = w1p  (:319)
+      PcgW3Params pp;
+      pp.n = n; pp.nslices = h->nslices; pp.max_iters = std::max(0, h->opt.cg_max_iters);
+      pp.rtol2 = h->opt.cg_rtol * h->opt.cg_rtol;
+      pp.sell_row = h->sell_row.as<int>(); pp.slice_off = h->slice_off.as<int>(); pp.slice_width = h->slice_width.as<int>();
+      pp.sell_col = h->sell_col.as<int>(); pp.sell_w3 = h->sell_w3.as<double4>(); pp.diag3 = h->diag3.as<double4>();
+      pp.B = h->pdW1P.as<double4>();
+      pp.X = h->pdDX.as<double4>(); pp.R = h->R.as<double4>(); pp.U = h->Z.as<double4>(); pp.W = h->AP.as<double4>();
+      pp.P = h->P.as<double4>(); pp.S = h->S.as<double4>(); pp.DINV = h->dinv3.as<double4>();
+      pp.partials = h->partials.as<double>(); pp.ctl = h->ctl.as<Ctl>();
+      const int grid = std::max(1, std::min(h->nslices, h->sms * h->pcg_blocks_per_sm));
+      void* args[] = {(void*)&pp};
+      IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_pcg_persistent_w3, dim3(grid), dim3(kPcgThreads), args, 0, h->stream));
+      h->launches++;
+    }
+    k_pd_direction<<<ge, 256, 0, h->stream>>>(h->I.as<int2>(), h->f, h->pdDX.as<double4>(), Y, h->pdU.as<double4>(),
+                                              h->pdAX.as<double4>(), h->pdL1.as<double4>(), h->pdL2.as<double4>(),
+                                              h->pdADX.as<double4>(), h->pdDU.as<double4>(), h->pdDL1.as<double4>(),
+                                              h->pdDL2.as<double4>(), h->pdEV.as<double4>(), m, ctl, part);
+    IRA_TRY(launch_check(h, "k_pd_direction"));
+    IRA_TRY(pd_At(h, h->pdATDV, 0));
+    for (int guard = 0; guard < 40; ++guard) {                        // back-tracking (:392-429), <= 33 rounds
+      k_pd_trial_edges<<<ge, 256, 0, h->stream>>>(Y, h->pdU.as<double4>(), h->pdAX.as<double4>(), h->pdL1.as<double4>(),
+                                                  h->pdL2.as<double4>(), h->pdADX.as<double4>(), h->pdDU.as<double4>(),
+                                                  h->pdDL1.as<double4>(), h->pdDL2.as<double4>(), m, ctl, part,
+                                                  h->pdtrial.as<double>());
+      IRA_TRY(launch_check(h, "k_pd_trial_edges"));
+      k_pd_trial_nodes<<<grid_nodes(h, n), 256, 0, h->stream>>>(h->pdATV.as<double4>(), h->pdATDV.as<double4>(), n, ctl, part,
+                                                               h->pdtrial.as<double>());
+      IRA_TRY(launch_check(h, "k_pd_trial_nodes"));
+      IRA_TRY(fetch_pdctl(h));
+      if (!h->h_pdctl->pending) break;
+    }
+    k_pd_accept_edges<<<ge, 256, 0, h->stream>>>(Y, h->pdU.as<double4>(), h->pdAX.as<double4>(), h->pdL1.as<double4>(),
+                                                 h->pdL2.as<double4>(), h->pdADX.as<double4>(), h->pdDU.as<double4>(),
+                                                 h->pdDL1.as<double4>(), h->pdDL2.as<double4>(), m, ctl, part);
+    IRA_TRY(launch_check(h, "k_pd_accept_edges"));
+    k_pd_accept_nodes<<<grid_nodes(h, n), 256, 0, h->stream>>>(h->pdX.as<double4>(), h->pdATV.as<double4>(),
+                                                              h->pdDX.as<double4>(), h->pdATDV.as<double4>(), n, ctl);
+    IRA_TRY(launch_check(h, "k_pd_accept_nodes"));
+    k_pd_rcent<<<ge, 256, 0, h->stream>>>(Y, h->pdU.as<double4>(), h->pdAX.as<double4>(), h->pdL1.as<double4>(),
+                                          h->pdL2.as<double4>(), m, 1, pdmaxiter, ctl, part);
+    IRA_TRY(launch_check(h, "k_pd_rcent"));
+    IRA_TRY(fetch_pdctl(h));
+    IRA_TRY(fetch_ctl(h));
+    *newton_cg_iters += h->h_ctl->cg_iters;
+    for (int k = 0; k < 3; ++k)
+      if (!(h->h_ctl->rnorm2[k] <= h->opt.cg_rtol * h->opt.cg_rtol * h->h_ctl->bnorm2[k])) { *hit_max += 1; break; }
+    const PdCtl& c = *h->h_pdctl;
+    if (!c.active[0] && !c.active[1] && !c.active[2]) break;
+  }
+  return IRA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+ira_status ira_resident_start(ira_handle h, int32_t mode) {
+  if (!h || (mode != 0 && mode != 1)) return IRA_ERR_INVALID_ARG;
+  h->start_mode = mode;
+  return IRA_OK;
+}
+
+ira_status ira_l1ra_resident(ira_handle h, int32_t max_iters, double change_th, int32_t* iters_out,
+                             double* runtime_s_out, ira_stats* stats) {
+  if (!h) return IRA_ERR_INVALID_ARG;
+  if (!h->uploaded) return IRA_ERR_NOT_UPLOADED;
+  if (h->opt.world_size > 1) { h->err = "l1ra is single-GPU in this version"; return IRA_ERR_INVALID_ARG; }
+  if (h->fmt_csr || h->pcg_blocks_per_sm <= 0) { h->err = "l1ra needs the SELL pattern and cooperative launch"; return IRA_ERR_INVALID_ARG; }
+  IRA_CUDA(h, cudaSetDevice(h->device));
+  const auto t0 = std::chrono::steady_clock::now();
+  const int launches0 = h->launches;
+  if (stats) memset(stats, 0, sizeof *stats);
+  IRA_TRY(l1ra_alloc(h));
+  const int n = h->n;
+  if (n > 0 && h->start_mode == 0)
+    IRA_CUDA(h, cudaMemcpyAsync(h->Q.p, h->Q0.p, sizeof(double4) * n, cudaMemcpyDeviceToDevice, h->stream));
+  IRA_CUDA(h, cudaMemsetAsync(h->weights.p, 0, sizeof(double) * h->m_pad, h->stream));
+  Ctl init;
+  memset(&init, 0, sizeof init);
+  *h->h_ctl = init;
+  IRA_CUDA(h, cudaMemcpyAsync(h->ctl.p, h->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, h->stream));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  double score = std::numeric_limits<double>::max();                       // :866
+  int iter = 0;
+  const int l1_step = 2;                                                   // :868 (never changes, App. A.6.7)
+  ira_status rc = IRA_OK;
+  while (score >= change_th && iter < max_iters) {                          // :877
+    IRA_TRY(run_residual(h, h->Q.as<double4>(), 0));                        // :885-887
+    int cg = 0, hit = 0;
+    if (h->m > 0) IRA_TRY(l1decode_pd_device(h, l1_step, &cg, &hit));       // :889-892
+    else IRA_CUDA(h, cudaMemsetAsync(h->pdX.p, 0, sizeof(double4) * (size_t)std::max(n, 1), h->stream));
+    k_update<<<grid_nodes(h, std::max(1, n - h->f), kRedThreads), kRedThreads, 0, h->stream>>>(
+        h->Q.as<double4>(), h->pdX.as<double4>(), n, h->f, h->ctl.as<Ctl>(), h->partials.as<double>());   // :894-902
+    IRA_TRY(launch_check(h, "k_update"));
+    IRA_TRY(fetch_ctl(h));
+    score = h->h_ctl->score;
+    if (stats && iter < IRA_STATS_MAX_ITERS) { stats->score[iter] = score; stats->cg_iters[iter] = cg; }
+    if (stats) { stats->cg_iters_total += cg; stats->cg_hit_max += hit; }
+    iter++;
+    if (!std::isfinite(score)) { if (n - h->f > 0) rc = IRA_ERR_NONFINITE; break; }
+  }
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (iters_out) *iters_out = iter;
+  if (runtime_s_out) *runtime_s_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (stats) { stats->irls_iters = iter; stats->kernel_launches = h->launches - launches0; }
+  if (rc == IRA_ERR_NONFINITE) h->err = "l1ra score became non-finite";
+  return rc;
+}
+
+ira_status ira_l1ra(ira_handle h, int64_t m, int64_t n_total, int32_t f, const int32_t* I_pairs, const double* QQ,
+                    int64_t ld_qq, double* Q, int64_t ld_q, int32_t max_iters, double change_th, int32_t* iters_out,
+                    double* runtime_s_out, ira_stats* stats) {
+  const auto t0 = std::chrono::steady_clock::now();
+  IRA_TRY(check_args(h, m, n_total, f, I_pairs, QQ, ld_qq, Q, ld_q));
+  IRA_TRY(ira_problem_upload(h, m, n_total, f, I_pairs, QQ, ld_qq, Q, ld_q));
+  const ira_status rc = ira_l1ra_resident(h, max_iters, change_th, iters_out, nullptr, stats);
+  if (rc != IRA_OK && rc != IRA_ERR_NONFINITE) return rc;
+  IRA_TRY(ira_problem_download(h, Q, ld_q, nullptr));
+  if (runtime_s_out) *runtime_s_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return rc;
 }
 
 }  // extern "C"

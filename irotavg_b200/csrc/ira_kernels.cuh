@@ -9,7 +9,8 @@
 //   Q        double4[n]           absolute rotations [x y z w]
 //   CSR of A^T A over ALL n nodes (rows of fixed nodes are empty, their x stays 0):
 //     rowptr int32[n+1], ent_col int32[nnz], ent_eid int32[nnz] (k for the +1 column, ~k for the
-//     -1 column of row k of A), ent_w2 double[nnz] (weights^2 of the entry's edge)
+//     -1 column of row k of A; bit 30 of k flags an entry make_A drops but make_AtA keeps, see
+//     k_csr_keys), ent_w2 double[nnz] (weights^2 of the entry's edge)
 //   node vectors X, R, Z, P, AP, B: double4[n] (c0, c1, c2, pad) for the 3 right-hand sides.
 //
 // Reference lines restated are cited per kernel (paths relative to the reference tree).
@@ -177,17 +178,21 @@ __global__ void k_fill_f64(double* __restrict__ p, double v, int64_t n) {
 // -------------------------------------------------------------------------------------------
 // Two candidate entries per edge k = (i, j):  slot 2k   -> row j, column i   (+1 column of A's row k)
 //                                             slot 2k+1 -> row i, column j   (-1 column)
-// Row j exists iff j >= f; row i exists iff j >= f AND i >= f (the `continue` at :771).
+// make_A (:755-780): row j exists iff j >= f; row i exists iff j >= f AND i >= f (the `continue` at :771).
+// make_AtA (:811-848, the Newton matrix of l1ra) has no such `continue`: an edge (free i, fixed j) still
+// loads H(i,i).  The pattern therefore keeps the row-i entry whenever i >= f and flags it (kEidQuirk)
+// when j < f: irls() gives flagged entries weight 0, l1ra's Newton matrix uses them.
 // Missing entries get the sentinel key n so a stable sort by key pushes them past the end.
+constexpr int kEidQuirk = 1 << 30;
+constexpr int kEidMask = kEidQuirk - 1;
 __global__ void k_csr_keys(const int2* __restrict__ I, int64_t m, int n, int f, int* __restrict__ keys,
                            int* __restrict__ vals, int* __restrict__ bad) {
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < m; k += (int64_t)gridDim.x * blockDim.x) {
     const int2 e = I[k];
     if (e.x < 0 || e.x >= n || e.y < 0 || e.y >= n) { atomicExch(bad, 1); keys[2 * k] = n; keys[2 * k + 1] = n; }
     else {
-      const bool has_j = e.y >= f, has_i = has_j && e.x >= f;
-      keys[2 * k] = has_j ? e.y : n;
-      keys[2 * k + 1] = has_i ? e.x : n;
+      keys[2 * k] = e.y >= f ? e.y : n;
+      keys[2 * k + 1] = e.x >= f ? e.x : n;
     }
     vals[2 * k] = (int)(2 * k);
     vals[2 * k + 1] = (int)(2 * k + 1);
@@ -195,7 +200,7 @@ __global__ void k_csr_keys(const int2* __restrict__ I, int64_t m, int n, int f, 
 }
 // keys sorted (stable => entries of a row are in increasing edge order => deterministic sums).
 __global__ void k_csr_finalize(const int* __restrict__ keys, const int* __restrict__ vals,
-                               const int2* __restrict__ I, int64_t two_m, int n, int* __restrict__ rowptr,
+                               const int2* __restrict__ I, int64_t two_m, int n, int f, int* __restrict__ rowptr,
                                int* __restrict__ ent_col, int* __restrict__ ent_eid) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p <= two_m; p += (int64_t)gridDim.x * blockDim.x) {
     const int kprev = p > 0 ? keys[p - 1] : -1;
@@ -208,7 +213,7 @@ __global__ void k_csr_finalize(const int* __restrict__ keys, const int* __restri
       const int src = vals[p];
       const int k = src >> 1;
       const int2 e = I[k];
-      if (src & 1) { ent_col[p] = e.y; ent_eid[p] = ~k; }   // row i: neighbour j, A(k,i) = -1
+      if (src & 1) { ent_col[p] = e.y; ent_eid[p] = ~(e.y < f ? (k | kEidQuirk) : k); }   // row i: neighbour j, A(k,i) = -1
       else         { ent_col[p] = e.x; ent_eid[p] = k; }    // row j: neighbour i, A(k,j) = +1
     }
   }
@@ -297,7 +302,9 @@ k_rhs_diag(const int* __restrict__ rowptr, const int* __restrict__ ent_eid, cons
       for (int e = rowptr[row] + sl; e < e1; e += LPR) {
         const int eid = ent_eid[e];
         const bool neg = eid < 0;
-        const double4 w = ldg256(wres + (neg ? ~eid : eid));
+        const int kk = neg ? ~eid : eid;
+        double4 w = ldg256(wres + (kk & kEidMask));
+        if (kk & kEidQuirk) w.w = 0.0;                       // make_A drops (free i, fixed j) edges
         ent_w2[e] = w.w;
         d += w.w;
         const double s = neg ? -w.w : w.w;

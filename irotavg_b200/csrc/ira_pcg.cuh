@@ -103,8 +103,9 @@ k_sell_rhs(const int* __restrict__ sell_row, const int* __restrict__ slice_off, 
       double w2 = 0.0;
       if (eid != kSellPad) {
         const bool neg = eid < 0;
-        const double4 w = ldg256(wres + (neg ? ~eid : eid));
-        w2 = w.w;
+        const int kk = neg ? ~eid : eid;
+        const double4 w = ldg256(wres + (kk & kEidMask));
+        w2 = (kk & kEidQuirk) ? 0.0 : w.w;                   // make_A drops (free i, fixed j) edges
         d += w2;
         const double sg = neg ? -w2 : w2;
         bx += sg * w.x; by += sg * w.y; bz += sg * w.z;

@@ -384,3 +384,159 @@ def geodesic_angles(Qa: np.ndarray, Qb: np.ndarray) -> np.ndarray:
 def geodesic_rms(Qa, Qb, f=0) -> float:
     a = geodesic_angles(np.asarray(Qa)[f:], np.asarray(Qb)[f:])
     return float(np.sqrt((a * a).mean())) if a.size else 0.0
+
+
+# --------------------------------------------------------------------------------------------
+# L1RA initial stage (NEXT row #1 of SURVEY 8(f)):  l1ra + l1decode_pd + make_AtA
+# --------------------------------------------------------------------------------------------
+def make_A_noquirk(n: int, f: int, I: np.ndarray):
+    """The incidence pattern behind make_AtA (ral/l1_irls.cpp:811-848): +1 at j-f if j>=f, -1 at i-f if
+    i>=f, INDEPENDENTLY of each other - make_AtA has no `continue`, so an edge (free i, fixed j) still
+    puts sigma on H(i,i) although make_A dropped it (App. A.6.1).  reshape(AtA*sigma) = A'^T diag(sigma) A'
+    up to the sign convention (AtA stores +1 on both diagonals and -1 off-diagonal)."""
+    import scipy.sparse as sp
+    m = I.shape[0]
+    hj = I[:, 1] >= f
+    hi = I[:, 0] >= f
+    rows = np.concatenate([np.nonzero(hj)[0], np.nonzero(hi)[0]])
+    cols = np.concatenate([I[hj, 1] - f, I[hi, 0] - f])
+    vals = np.concatenate([np.ones(hj.sum()), -np.ones(hi.sum())])
+    return sp.csc_matrix((vals, (rows, cols)), shape=(m, n - f))
+
+
+def l1decode_pd(x0, A, y, pdmaxiter, Ah, newton="direct", pcg_rtol=1e-13, trace=None):
+    """Primal-dual interior-point L1 regression min ||A x - y||_1, restating ral/l1_irls.cpp:228-468
+    line by line (l1-magic's l1decode_pd).  `Ah` is the pattern of make_AtA (make_A_noquirk): the
+    Newton matrix is H = Ah^T diag(sigx) Ah (:308-319), solved exactly by UMFPACK in the reference
+    (linsolve, :131-184; third-party, unpinned) and here by sparse LU ('direct') or Jacobi-PCG ('pcg')."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    PDTOL, alpha, beta, mu = 1e-3, 0.01, 0.5, 10.0                         # :231-238
+    n, m = x0.size, y.size
+    At = A.T.tocsr()
+    x = x0.copy()
+    Ax = A @ x
+    yab = np.abs(y - Ax)
+    u = 0.95 * yab + 0.10 * yab.max()                                      # :248-253
+    fu1 = Ax - y - u
+    fu2 = -Ax + y - u
+    lamu1 = -1.0 / fu1
+    lamu2 = -1.0 / fu2
+    Atv = At @ (lamu1 - lamu2)                                             # :262
+    sdg = -(fu1 @ lamu1 + fu2 @ lamu2)
+    tau = mu * 2 * m / sdg                                                 # :265
+    rcent = np.concatenate([-lamu1 * fu1, -lamu2 * fu2]) - 1.0 / tau
+    rdual_n = Atv.copy()                                                   # gradf0 = [0; 1]
+    rdual_m = 1.0 - lamu1 - lamu2
+    resnorm = np.sqrt(rdual_n @ rdual_n + rdual_m @ rdual_m + rcent @ rcent)
+    pditer = 0
+    done = (sdg < PDTOL) or (pditer >= pdmaxiter)                          # :284
+    xp = x.copy()       # the reference returns an unassigned Vec when the loop never runs (A.6.7)
+    Aht = Ah.T.tocsr()
+    while not done:
+        pditer += 1
+        w2 = -1.0 - (1.0 / tau) * (1.0 / fu1 + 1.0 / fu2)                  # :293
+        sig1 = -lamu1 / fu1 - lamu2 / fu2
+        sig2 = lamu1 / fu1 - lamu2 / fu2
+        sigx = sig1 - sig2 ** 2 / sig1                                     # :296-298
+        w1 = -(1.0 / tau) * (At @ (-1.0 / fu1 + 1.0 / fu2))                # :301-302
+        w1p = w1 - At @ ((sig2 / sig1) * w2)                               # :305-306
+        H = (Aht @ sp.diags(sigx) @ Ah).tocsc()                            # :308-317
+        if newton == "direct":
+            lu = spla.splu(H)
+            dx = lu.solve(w1p)
+            dx += lu.solve(w1p - H @ dx)
+        else:
+            dx = pcg_jacobi(H.tocsr(), H.diagonal(), w1p[:, None], rtol=pcg_rtol)[0][:, 0]
+        Adx = A @ dx                                                       # :324
+        du = (w2 - sig2 * Adx) / sig1                                      # :327
+        dlamu1 = -(lamu1 / fu1) * (Adx - du) - lamu1 - (1.0 / tau) / fu1   # :330-333
+        dlamu2 = (lamu2 / fu2) * (Adx + du) - lamu2 - (1.0 / tau) / fu2    # :336-339
+        Atdv = At @ (dlamu1 - dlamu2)                                      # :342
+        s = 1.0                                                            # :347-381
+        neg = dlamu1 < 0
+        if neg.any():
+            s = min(s, (-lamu1[neg] / dlamu1[neg]).min())
+        neg = dlamu2 < 0
+        if neg.any():
+            s = min(s, (-lamu2[neg] / dlamu2[neg]).min())
+        d1 = Adx - du
+        pos = d1 > 0
+        if pos.any():
+            s = min(s, (-fu1[pos] / d1[pos]).min())
+        d2 = -Adx - du
+        pos = d2 > 0
+        if pos.any():
+            s = min(s, (-fu2[pos] / d2[pos]).min())
+        s *= 0.99
+        suffdec = False
+        backiter = 0
+        while not suffdec:                                                 # :392-429
+            xp = x + s * dx
+            up = u + s * du
+            Axp = Ax + s * Adx
+            Atvp = Atv + s * Atdv
+            lamu1p = lamu1 + s * dlamu1
+            lamu2p = lamu2 + s * dlamu2
+            fu1p = Axp - y - up
+            fu2p = -Axp + y - up
+            rdp_n = Atvp
+            rdp_m = 1.0 - lamu1p - lamu2p
+            rcp = np.concatenate([-lamu1p * fu1p, -lamu2p * fu2p]) - 1.0 / tau
+            suffdec = np.sqrt(rdp_n @ rdp_n + rdp_m @ rdp_m + rcp @ rcp) <= (1 - alpha * s) * resnorm
+            s *= beta
+            backiter += 1
+            if backiter > 32:                                              # :423-428
+                return x.copy()
+        x, u, Ax, Atv = xp, up, Axp, Atvp                                  # :432-442
+        lamu1, lamu2, fu1, fu2 = lamu1p, lamu2p, fu1p, fu2p
+        sdg = -(fu1 @ lamu1 + fu2 @ lamu2)                                 # :446
+        tau = mu * 2 * m / sdg
+        rcent = np.concatenate([-lamu1 * fu1, -lamu2 * fu2]) - 1.0 / tau
+        resnorm = np.sqrt(rdp_n @ rdp_n + rdp_m @ rdp_m + rcent @ rcent)   # rdual = rdp (:455-458)
+        if trace is not None:
+            trace.append(dict(pditer=pditer, backiter=backiter, s=s / beta, sdg=sdg, tau=tau, resnorm=resnorm,
+                              sigx_min=float(sigx.min()), sigx_max=float(sigx.max())))
+        done = (sdg < PDTOL) or (pditer >= pdmaxiter)
+    return xp
+
+
+@dataclass
+class L1raResult:
+    Q: np.ndarray
+    iters: int
+    runtime: float
+    scores: list = field(default_factory=list)
+    trace: list = field(default_factory=list)
+
+
+def l1ra(QQ, I, A, Q, f, max_iters, change_th, newton="direct", pcg_rtol=1e-13) -> L1raResult:
+    """irotavg::l1ra, ral/l1_irls.cpp:851-912.  l1_step stays 2 for ever: the `if (score<change_th)` at
+    :879 is unreachable because the loop condition already requires score >= change_th (A.6.7)."""
+    tic = time.perf_counter()
+    QQ = np.asarray(QQ, dtype=np.float64)
+    I = np.asarray(I, dtype=np.int64).reshape(-1, 2)
+    Q = np.array(Q, dtype=np.float64, copy=True)
+    ntot = Q.shape[0]
+    n = ntot - f
+    if A is None:
+        A = make_A(ntot, f, I)
+    A = A.tocsr()
+    Ah = make_A_noquirk(ntot, f, I).tocsr()
+    score = np.finfo(np.float64).max
+    it = 0
+    l1_step = 2
+    scores, trace = [], []
+    while (score >= change_th or l1_step < 2) and it < max_iters:          # :877
+        w = log_map(delta_rel(I, QQ, Q))                                   # :885-887
+        W = np.zeros((n, 4))
+        for c in range(3):                                                 # :890-892
+            tr = []
+            W[:, c] = l1decode_pd(np.zeros(n), A, w[:, c].copy(), l1_step, Ah, newton, pcg_rtol, tr)
+            trace.append(tr)
+        score = float(np.sqrt((W[:, :3] ** 2).sum(axis=1)).mean())         # :894
+        exp_map(W)
+        Q[f:] = quat_mult(Q[f:], W)                                        # :899-902
+        it += 1
+        scores.append(score)
+    return L1raResult(Q=Q, iters=it, runtime=time.perf_counter() - tic, scores=scores, trace=trace)

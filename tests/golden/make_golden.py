@@ -6,7 +6,8 @@
 bundled_graph.npz: the parsed reference fixture ral/data/ravg_input.txt (m=3655, n=1832, f=1) as
   ral/test.cpp:161-247 reads it, its init_mst start (ral/test.cpp:285-286), and the oracle's
   irls() outputs (ral/test.cpp:300 with the CLI defaults: 50 iterations max, change_th 1e-3,
-  sigma 5 deg) for L2 / L1 / Geman-McClure / Huber, plus a 10-iteration change_th=-1 L1 run.
+  sigma 5 deg) for L2 / L1 / Geman-McClure / Huber, plus a 10-iteration change_th=-1 L1 run, plus the
+  CLI's whole default flow init_mst -> l1ra(5 iterations, 1e-3) -> irls(Geman-McClure) -> quat_normalised.
 small_costs.npz: a 60-node graph with outliers, f=3, edges in both orientations (exercises
   make_A's dropped-edge rule), oracle outputs after 6 iterations for all 14 costs (sigma 5 deg;
   20 deg for Talwar, whose hard threshold at 5 deg makes the system singular on this graph).
@@ -43,6 +44,15 @@ def bundled():
     out["l1x10_Q"] = r.Q
     out["l1x10_weights"] = r.weights
     out["l1x10_scores"] = np.array(r.scores)
+    # the CLI's full flow with its defaults (ral/test.cpp:285-302): init_mst -> l1ra(5, 1e-3) -> irls(GM, 5 deg, 50, 1e-3)
+    la = O.l1ra(QQ, I, None, Qmst, f, 5, 1e-3)
+    out["l1ra_Q"] = la.Q
+    out["l1ra_scores"] = np.array(la.scores)
+    out["l1ra_iters"] = np.int32(la.iters)
+    r = O.irls(QQ, I, None, O.GEMAN_MCCLURE, SIGMA, la.Q, f, 50, 1e-3, solver="direct")
+    out["cli_Q"] = O.quat_normalised(r.Q.copy(), f)
+    out["cli_weights"] = r.weights
+    out["cli_irls_iters"] = np.int32(r.iters)
     np.savez_compressed(os.path.join(HERE, "bundled_graph.npz"), **out)
     print("bundled:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items() if k.endswith("scores")})
 
