@@ -152,6 +152,25 @@ ira_status ira_l1ra_resident(ira_handle h, int32_t max_iters, double change_th,
  * mode 1: they continue from the current device Q (l1ra followed by irls, like both callers). */
 ira_status ira_resident_start(ira_handle h, int32_t mode);
 
+/* ---- irotavg::init_mst  (ral/l1_irls.hpp:89-90, ral/l1_irls.cpp:915-979) ----------------------
+ * Spanning-tree start: the reference sweeps the edge list in order until every node is flagged; the
+ * tree (and so the result) depends on the edge order.  The device reproduces exactly that tree
+ * (time-stamp relaxation, irotavg_b200/csrc/ira_mst.cuh) and the same one product per node.  Rows
+ * [0, f_init) of Q are kept (ral/test.cpp:285-286 passes max(#given rotations, f)); the others are
+ * overwritten.  IRA_ERR_NOT_SPANNING when the edges do not reach every node (:970-977; Q undefined).
+ * The resident form acts on the uploaded problem: both the restart copy Q0 and the current Q get the
+ * tree start, so that ira_l1ra_resident / ira_irls_resident follow without crossing PCIe. */
+typedef struct ira_mst_stats {
+  int32_t passes_label;       /* relaxation passes until the time stamps were final          */
+  int32_t passes_propagate;   /* passes of the rotation propagation                          */
+  int32_t unreached;          /* nodes not spanned                                           */
+  double  t_ms;               /* device time (CUDA events)                                   */
+} ira_mst_stats;
+ira_status ira_init_mst(ira_handle h, int64_t m, int64_t n_total, int32_t f_init,
+                        const int32_t* I_pairs, const double* QQ, int64_t ld_qq,
+                        double* Q, int64_t ld_q, ira_mst_stats* stats /* may be NULL */);
+ira_status ira_init_mst_resident(ira_handle h, int32_t f_init, ira_mst_stats* stats /* may be NULL */);
+
 /* ---- irotavg::make_A  (ral/l1_irls.hpp:92, ral/l1_irls.cpp:755-780) -------------------------
  * Host helper (no device): writes per edge the two column indices of row k of A, or -1:
  * col_plus[k] = j-f if j >= f else -1;  col_minus[k] = i-f if (j >= f and i >= f) else -1. */

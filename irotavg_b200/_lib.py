@@ -65,6 +65,12 @@ class Stats(C.Structure):
     ]
 
 
+class MstStats(C.Structure):
+    """ira_mst_stats of include/ira.h."""
+    _fields_ = [("passes_label", C.c_int32), ("passes_propagate", C.c_int32), ("unreached", C.c_int32),
+                ("t_ms", C.c_double)]
+
+
 class IraError(RuntimeError):
     def __init__(self, status: int, text: str):
         super().__init__(f"ira status {status}: {text}")
@@ -111,6 +117,8 @@ def load():
         "ira_l1ra": (i32, [H, i64, i64, i32, pi32, pf64, i64, pf64, i64, i32, f64, pi32, pf64, C.POINTER(Stats)]),
         "ira_l1ra_resident": (i32, [H, i32, f64, pi32, pf64, C.POINTER(Stats)]),
         "ira_resident_start": (i32, [H, i32]),
+        "ira_init_mst": (i32, [H, i64, i64, i32, pi32, pf64, i64, pf64, i64, C.POINTER(MstStats)]),
+        "ira_init_mst_resident": (i32, [H, i32, C.POINTER(MstStats)]),
     }
     for name, (res, args) in sig.items():
         if not hasattr(lib, name):

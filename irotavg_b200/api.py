@@ -14,7 +14,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib
-from ._lib import IraError, Options, Stats
+from ._lib import IraError, MstStats, Options, Stats
 
 # enum Cost (ral/l1_irls.hpp:56-57)
 L2, L1, L15, L05, Geman_McClure, Huber, Pseudo_Huber, Andrews, Bisquare, Cauchy, Fair, Logistic, \
@@ -204,6 +204,26 @@ class Solver:
         """False: resident calls restart from the uploaded Q0; True: continue from the current device Q."""
         self._check(self._lib.ira_resident_start(self._h, 1 if from_current else 0), self._h)
 
+    # -- irotavg::init_mst --------------------------------------------------------------------
+    def init_mst(self, Q, QQ, I, f):
+        """irotavg::init_mst (ral/l1_irls.hpp:89-90; argument order of the reference).  Returns
+        (Q_new, stats dict); Q is not modified."""
+        QQf = _colmajor(QQ, 4)
+        Qf = np.array(_colmajor(Q, 4), order="F", copy=True)
+        Ip = _pairs(I)
+        m, n = QQf.shape[0], Qf.shape[0]
+        st = MstStats()
+        self._check(self._lib.ira_init_mst(self._h, m, n, int(f), _pi(Ip), _pd(QQf), max(m, 1), _pd(Qf), max(n, 1),
+                                           C.byref(st)), self._h)
+        return np.ascontiguousarray(Qf), {"passes_label": st.passes_label, "passes_propagate": st.passes_propagate,
+                                          "unreached": st.unreached, "ms": st.t_ms}
+
+    def init_mst_resident(self, f_init):
+        st = MstStats()
+        self._check(self._lib.ira_init_mst_resident(self._h, int(f_init), C.byref(st)), self._h)
+        return {"passes_label": st.passes_label, "passes_propagate": st.passes_propagate,
+                "unreached": st.unreached, "ms": st.t_ms}
+
     # -- device-resident variant --------------------------------------------------------------
     def upload(self, QQ, I, Q0, f):
         QQf = _colmajor(QQ, 4)
@@ -289,6 +309,11 @@ def l1ra(QQ, I, A, Q, f, max_iters, change_th):
     """irotavg::l1ra.  Returns (Q, iter, runtime)."""
     Qn, info = _solver().l1ra(QQ, I, A, Q, f, max_iters, change_th)
     return Qn, info.iters, info.runtime
+
+
+def init_mst(Q, QQ, I, f):
+    """irotavg::init_mst.  Returns the initialised Q."""
+    return _solver().init_mst(Q, QQ, I, f)[0]
 
 
 def make_A(n, f, I):

@@ -26,6 +26,26 @@ NVCC_FLAGS = [
 ]
 
 
+HOST = os.path.join(HERE, "host")
+CLI = os.path.join(LIBDIR, "l1_irls")
+
+
+def build_cli(force: bool = False) -> str:
+    """The `l1_irls` executable (host/l1_irls_cli.cpp: the reference's ral/test.cpp flow over the adapter
+    header), linked against libira.so with an rpath relative to the executable."""
+    src = os.path.join(HOST, "l1_irls_cli.cpp")
+    deps = [src, os.path.join(HOST, "l1_irls.hpp"), os.path.join(INCLUDE, "ira.h")]
+    if (not force and os.path.exists(CLI)
+            and all(os.path.getmtime(CLI) >= os.path.getmtime(d) for d in deps + [LIB])):
+        return CLI
+    cmd = ["g++", "-std=c++11", "-O2", "-Wall", "-I", INCLUDE, "-I", HOST, src, "-o", CLI, "-L", LIBDIR, "-lira",
+           "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + (res.stdout + res.stderr)[-4000:])
+    return CLI
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -54,6 +74,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as fh:
             if fh.read().strip() == digest:
+                build_cli()
                 return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-o", LIB, *units, "-ldl"]
@@ -67,6 +88,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print(log)
     with open(STAMP, "w") as fh:
         fh.write(digest)
+    build_cli(force=True)
     return LIB
 
 

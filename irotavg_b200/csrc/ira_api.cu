@@ -23,6 +23,7 @@
 #include "ira_kernels.cuh"
 #include "ira_pcg.cuh"
 #include "ira_l1ra.cuh"
+#include "ira_mst.cuh"
 
 using namespace ira;
 
@@ -94,6 +95,7 @@ struct ira_context {
   DevBuf pdU, pdAX, pdL1, pdL2, pdADX, pdDU, pdDL1, pdDL2, pdEV, pdSIGX, sell_w3;
   DevBuf pdX, pdATV, pdATDV, pdW1P, pdDX, diag3, dinv3, pdctl, pdtrial;
   PdCtl* h_pdctl = nullptr;  // pinned
+  DevBuf mst_label, mst_label2, mst_order, mst_order2, mst_done, mst_ctl;   // init_mst (ira_mst.cuh)
   int start_mode = 0;        // 0: resident calls restart from the uploaded Q0, 1: continue from the current Q
   int nslices = 0, npos = 0;
   int64_t sell_total = 0;
@@ -714,7 +716,8 @@ ira_status ira_destroy(ira_handle h) {
                     &h->slice_off, &h->slice_width, &h->slice_cnt, &h->sell_col, &h->sell_eid, &h->sell_w2,
                     &h->R2, &h->S2, &h->pdU, &h->pdAX, &h->pdL1, &h->pdL2, &h->pdADX, &h->pdDU, &h->pdDL1, &h->pdDL2, &h->pdEV,
                     &h->pdSIGX, &h->sell_w3, &h->pdX, &h->pdATV, &h->pdATDV, &h->pdW1P, &h->pdDX, &h->diag3, &h->dinv3,
-                    &h->pdctl, &h->pdtrial, &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs})
+                    &h->pdctl, &h->pdtrial, &h->mst_label, &h->mst_label2, &h->mst_order, &h->mst_order2, &h->mst_done,
+                    &h->mst_ctl, &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs})
     b->release();
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -1262,6 +1265,108 @@ ira_status ira_l1ra(ira_handle h, int64_t m, int64_t n_total, int32_t f, const i
   IRA_TRY(ira_problem_download(h, Q, ld_q, nullptr));
   if (runtime_s_out) *runtime_s_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return rc;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// irotavg::init_mst  (ral/l1_irls.hpp:89-90, ral/l1_irls.cpp:915-979) on the device, ira_mst.cuh
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+ira_status ira_init_mst_resident(ira_handle h, int32_t f_init, ira_mst_stats* stats) {
+  if (!h) return IRA_ERR_INVALID_ARG;
+  if (!h->uploaded) return IRA_ERR_NOT_UPLOADED;
+  if (f_init < 1) { h->err = "init_mst: f < 1 (ral/l1_irls.cpp:917)"; return IRA_ERR_INVALID_ARG; }
+  IRA_CUDA(h, cudaSetDevice(h->device));
+  const int n = h->n;
+  const int64_t m = h->m;
+  if (stats) memset(stats, 0, sizeof *stats);
+  if (n <= 1) return IRA_OK;                                              // count == n at once (:925)
+  IRA_CUDA(h, h->mst_label.reserve(sizeof(unsigned long long) * (size_t)n));
+  IRA_CUDA(h, h->mst_label2.reserve(sizeof(unsigned long long) * (size_t)n));
+  IRA_CUDA(h, h->mst_order.reserve(sizeof(int) * (size_t)n));
+  IRA_CUDA(h, h->mst_order2.reserve(sizeof(int) * (size_t)n));
+  IRA_CUDA(h, h->mst_done.reserve(sizeof(int) * (size_t)n));
+  IRA_CUDA(h, h->mst_ctl.reserve(sizeof(MstCtl)));
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  IRA_CUDA(h, cudaEventCreate(&ev0));
+  IRA_CUDA(h, cudaEventCreate(&ev1));
+  IRA_CUDA(h, cudaEventRecord(ev0, h->stream));
+  k_mst_init<<<cdiv(n, 256), 256, 0, h->stream>>>(h->mst_label.as<unsigned long long>(), h->mst_done.as<int>(),
+                                                 h->mst_order.as<int>(), n, h->mst_ctl.as<MstCtl>());
+  IRA_TRY(launch_check(h, "k_mst_init"));
+  int per_sm = 0;
+  IRA_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mst_labels, 256, 0));
+  per_sm = std::max(1, std::min(per_sm, 4));
+  {
+    const int2* I = h->I.as<int2>();
+    int64_t mm = m;
+    unsigned long long* lab = h->mst_label.as<unsigned long long>();
+    MstCtl* ctl = h->mst_ctl.as<MstCtl>();
+    const int grid = std::max(1, std::min(cdiv(cdiv(std::max<int64_t>(m, 1), kMstEdgeChunk), 256), h->sms * per_sm));
+    void* args[] = {(void*)&I, (void*)&mm, (void*)&lab, (void*)&ctl};
+    IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_mst_labels, dim3(grid), dim3(256), args, 0, h->stream));
+    h->launches++;
+  }
+  {                                                                       // nodes in the order the sweeps flag them
+    size_t tmp_bytes = 0;
+    IRA_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->mst_label.as<unsigned long long>(),
+                                                h->mst_label2.as<unsigned long long>(), h->mst_order.as<int>(),
+                                                h->mst_order2.as<int>(), n, 0, 64, h->stream));
+    IRA_CUDA(h, h->cubtmp.reserve(tmp_bytes));
+    IRA_CUDA(h, cub::DeviceRadixSort::SortPairs(h->cubtmp.p, tmp_bytes, h->mst_label.as<unsigned long long>(),
+                                                h->mst_label2.as<unsigned long long>(), h->mst_order.as<int>(),
+                                                h->mst_order2.as<int>(), n, 0, 64, h->stream));
+    h->launches += 8;
+  }
+  IRA_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mst_propagate, 256, 0));
+  per_sm = std::max(1, std::min(per_sm, 4));
+  {
+    const int2* I = h->I.as<int2>();
+    const double* QQ = h->QQ.as<double>();
+    int64_t ld = h->m_pad;
+    const int* order = h->mst_order2.as<int>();
+    const unsigned long long* lab = h->mst_label.as<unsigned long long>();
+    int nn = n, fi = f_init;
+    double4* Q = h->Q0.as<double4>();
+    int* done = h->mst_done.as<int>();
+    MstCtl* ctl = h->mst_ctl.as<MstCtl>();
+    const int grid = std::max(1, std::min(cdiv(cdiv(n, kMstNodeChunk), 256), h->sms * per_sm));
+    void* args[] = {(void*)&I, (void*)&QQ, (void*)&ld, (void*)&order, (void*)&lab, (void*)&nn, (void*)&fi,
+                    (void*)&Q, (void*)&done, (void*)&ctl};
+    IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_mst_propagate, dim3(grid), dim3(256), args, 0, h->stream));
+    h->launches++;
+  }
+  IRA_CUDA(h, cudaMemcpyAsync(h->Q.p, h->Q0.p, sizeof(double4) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+  IRA_CUDA(h, cudaEventRecord(ev1, h->stream));
+  MstCtl host;
+  IRA_CUDA(h, cudaMemcpyAsync(&host, h->mst_ctl.p, sizeof host, cudaMemcpyDeviceToHost, h->stream));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev0, ev1);
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  if (stats) {
+    stats->passes_label = host.passes_label; stats->passes_propagate = host.passes_prop;
+    stats->unreached = host.unreached; stats->t_ms = ms;
+  }
+  if (host.unreached > 0) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "Relative rotations DO NOT SPAN all the nodes in the VIEW GRAPH\n"
+             "Number of nodes in Spanning Tree = %d", n - host.unreached);
+    h->err = buf;
+    return IRA_ERR_NOT_SPANNING;
+  }
+  return IRA_OK;
+}
+
+ira_status ira_init_mst(ira_handle h, int64_t m, int64_t n_total, int32_t f_init, const int32_t* I_pairs,
+                        const double* QQ, int64_t ld_qq, double* Q, int64_t ld_q, ira_mst_stats* stats) {
+  IRA_TRY(check_args(h, m, n_total, f_init, I_pairs, QQ, ld_qq, Q, ld_q));
+  IRA_TRY(ira_problem_upload(h, m, n_total, f_init, I_pairs, QQ, ld_qq, Q, ld_q));
+  IRA_TRY(ira_init_mst_resident(h, f_init, stats));
+  return ira_problem_download(h, Q, ld_q, nullptr);
 }
 
 }  // extern "C"

@@ -159,6 +159,42 @@ inline void irls(const MatT& QQ, const I_t& I, const SpMatT& /*A*/, CostT cost, 
   if (it >= max_iters) std::cout << " Max Iteration" << std::endl;                                // :746-749
 }
 
+// void l1ra(QQ, I, A, Q, f, max_iters, change_th, iter, runtime)
+//   - ral/l1_irls.hpp:98-101, ral/l1_irls.cpp:851-912.  Q rows [f, n) are updated in place.
+template <class MatT, class SpMatT>
+inline void l1ra(const MatT& QQ, const I_t& I, const SpMatT& /*A*/, MatT& Q, const int f, const int max_iters,
+                 double change_th, int& iter, double& runtime) {
+  const int64_t m = (int64_t)QQ.rows(), n = (int64_t)Q.rows();
+  if ((int64_t)I.size() != m) {
+    std::cerr << "l1ra: I and QQ disagree on the number of connections" << std::endl;
+    std::exit(-1);
+  }
+  const std::vector<int32_t> flat = detail::flatten(I);
+  int32_t it = 0;
+  double rt = 0.0;
+  ira_status s = ira_l1ra(detail::handle(), m, n, f, flat.data(), QQ.data(), m > 0 ? m : 1, Q.data(), n > 0 ? n : 1,
+                          max_iters, change_th, &it, &rt, nullptr);
+  detail::check(s, "l1ra");
+  iter = it;
+  runtime = rt;
+}
+
+// void init_mst(Q, QQ, I, f)   - ral/l1_irls.hpp:89-90, ral/l1_irls.cpp:915-979.  Rows [0, f) of Q are
+// kept, the others are overwritten with the spanning-tree start (same tree as the reference's edge sweeps).
+template <class MatT>
+inline void init_mst(MatT& Q, const MatT& QQ, const I_t& I, const int f) {
+  const int64_t m = (int64_t)QQ.rows(), n = (int64_t)Q.rows();
+  const std::vector<int32_t> flat = detail::flatten(I);
+  ira_status s = ira_init_mst(detail::handle(), m, n, f, flat.data(), QQ.data(), m > 0 ? m : 1, Q.data(),
+                              n > 0 ? n : 1, nullptr);
+  if (s == IRA_ERR_NOT_SPANNING) {                                                                 // :970-977
+    std::cerr << ira_last_error(detail::handle()) << "\nConnected Nodes are given as output\n"
+              << "Remove extra nodes and retry." << std::endl;
+    std::exit(-1);
+  }
+  detail::check(s, "init_mst");
+}
+
 // void quat_normalised(Q, f)   - ral/l1_irls.hpp:112, ral/l1_irls.cpp:982-991
 template <class MatT>
 inline void quat_normalised(MatT& Q, const int f) {
@@ -173,6 +209,8 @@ inline void quat_normalised(MatT& Q, const int f) {
 namespace irotavg {
 inline SpMat make_A(const int n, const int f, const I_t& I) { return ira_b200::make_A_as<SpMat>(n, f, I); }
 using ira_b200::irls;
+using ira_b200::l1ra;
+using ira_b200::init_mst;
 using ira_b200::quat_normalised;
 }  // namespace irotavg
 #endif
