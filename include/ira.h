@@ -152,6 +152,17 @@ ira_status ira_l1ra_resident(ira_handle h, int32_t max_iters, double change_th,
  * mode 1: they continue from the current device Q (l1ra followed by irls, like both callers). */
 ira_status ira_resident_start(ira_handle h, int32_t mode);
 
+/* ---- l1ra then irls on ONE upload: what ViewGraph::rotAvg (src/ViewGraph.cpp:1400-1417) and the CLI
+ * (ral/test.cpp:288-300) do back to back.  Same arguments as the two calls; the rotations stay on the
+ * device between the stages.  *runtime_s_out is the wall time of the whole call. */
+ira_status ira_l1ra_irls(ira_handle h, int64_t m, int64_t n_total, int32_t f,
+                         const int32_t* I_pairs, const double* QQ, int64_t ld_qq,
+                         double* Q, int64_t ld_q,
+                         int32_t l1_max_iters, double l1_change_th,
+                         int32_t cost, double sigma, int32_t irls_max_iters, double irls_change_th,
+                         double* weights, int32_t* l1_iters_out, int32_t* irls_iters_out,
+                         double* runtime_s_out, ira_stats* irls_stats /* may be NULL */);
+
 /* ---- irotavg::init_mst  (ral/l1_irls.hpp:89-90, ral/l1_irls.cpp:915-979) ----------------------
  * Spanning-tree start: the reference sweeps the edge list in order until every node is flagged; the
  * tree (and so the result) depends on the edge order.  The device reproduces exactly that tree

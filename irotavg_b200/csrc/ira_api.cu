@@ -1370,3 +1370,28 @@ ira_status ira_init_mst(ira_handle h, int64_t m, int64_t n_total, int32_t f_init
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// l1ra followed by irls on one upload: the call sequence of both callers
+// (ral/test.cpp:295-300, src/ViewGraph.cpp:1407-1417)
+// ---------------------------------------------------------------------------------------------
+extern "C" ira_status ira_l1ra_irls(ira_handle h, int64_t m, int64_t n_total, int32_t f, const int32_t* I_pairs,
+                                    const double* QQ, int64_t ld_qq, double* Q, int64_t ld_q, int32_t l1_max_iters,
+                                    double l1_change_th, int32_t cost, double sigma, int32_t irls_max_iters,
+                                    double irls_change_th, double* weights, int32_t* l1_iters_out,
+                                    int32_t* irls_iters_out, double* runtime_s_out, ira_stats* irls_stats) {
+  const auto t0 = std::chrono::steady_clock::now();
+  IRA_TRY(check_args(h, m, n_total, f, I_pairs, QQ, ld_qq, Q, ld_q));
+  if (m > 0 && !weights) { h->err = "null weights"; return IRA_ERR_INVALID_ARG; }
+  if (cost < 0 || cost >= kNumCosts) { h->err = "Unknown cost!!"; return IRA_ERR_UNKNOWN_COST; }
+  IRA_TRY(ira_problem_upload(h, m, n_total, f, I_pairs, QQ, ld_qq, Q, ld_q));
+  ira_status rc = ira_l1ra_resident(h, l1_max_iters, l1_change_th, l1_iters_out, nullptr, nullptr);
+  if (rc != IRA_OK && rc != IRA_ERR_NONFINITE) return rc;
+  h->start_mode = 1;                                       // irls continues from l1ra's rotations
+  rc = ira_irls_resident(h, cost, sigma, irls_max_iters, irls_change_th, irls_iters_out, nullptr, irls_stats);
+  h->start_mode = 0;
+  if (rc != IRA_OK && rc != IRA_ERR_NONFINITE) return rc;
+  IRA_TRY(ira_problem_download(h, Q, ld_q, weights));
+  if (runtime_s_out) *runtime_s_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return rc;
+}
