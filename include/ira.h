@@ -71,7 +71,10 @@ typedef struct ira_options {
                               +4 = persistent kernel keeps its vectors in HBM even when one row per
                               lane would let them live in registers (A/B measurement)               */
   int32_t spmv_variant;    /* experiment knob: gather flavour / unroll of the SELL SpMV (0 = default)  */
-  int32_t reserved[5];
+  int32_t small_path;      /* window-sized problems (n_total <= 64, 1 <= n_free <= 32, m <= 256) in
+                              ira_l1ra_irls run as ONE single-block kernel with dense Cholesky solves
+                              (irotavg_b200/csrc/ira_small.cuh): 0 = yes (default), 1 = never              */
+  int32_t reserved[4];
 } ira_options;
 
 #define IRA_STATS_MAX_ITERS 256
@@ -154,7 +157,9 @@ ira_status ira_resident_start(ira_handle h, int32_t mode);
 
 /* ---- l1ra then irls on ONE upload: what ViewGraph::rotAvg (src/ViewGraph.cpp:1400-1417) and the CLI
  * (ral/test.cpp:288-300) do back to back.  Same arguments as the two calls; the rotations stay on the
- * device between the stages.  *runtime_s_out is the wall time of the whole call. */
+ * device between the stages.  *runtime_s_out is the wall time of the whole call.  Window-sized problems
+ * (see ira_options.small_path) take a single launch with exact dense solves; irls_stats then carries
+ * irls_iters, the first 8 scores and kernel_launches = 1. */
 ira_status ira_l1ra_irls(ira_handle h, int64_t m, int64_t n_total, int32_t f,
                          const int32_t* I_pairs, const double* QQ, int64_t ld_qq,
                          double* Q, int64_t ld_q,

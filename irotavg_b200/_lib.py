@@ -20,7 +20,7 @@ SYMBOLS = [
     "ira_abi_version", "ira_device_count", "ira_get_stream", "ira_irls", "ira_problem_upload", "ira_irls_resident",
     "ira_problem_download", "ira_make_A", "ira_quat_normalised", "ira_probe_residual",
     "ira_probe_laplacian_apply", "ira_probe_time_kernel", "ira_comm_unique_id", "ira_comm_init",
-    "ira_l1ra", "ira_l1ra_resident", "ira_resident_start",
+    "ira_l1ra", "ira_l1ra_resident", "ira_resident_start", "ira_l1ra_irls", "ira_init_mst", "ira_init_mst_resident",
 ]
 
 
@@ -37,7 +37,8 @@ class Options(C.Structure):
         ("profile", C.c_int32),
         ("solver", C.c_int32),
         ("spmv_variant", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("small_path", C.c_int32),
+        ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -117,6 +118,8 @@ def load():
         "ira_l1ra": (i32, [H, i64, i64, i32, pi32, pf64, i64, pf64, i64, i32, f64, pi32, pf64, C.POINTER(Stats)]),
         "ira_l1ra_resident": (i32, [H, i32, f64, pi32, pf64, C.POINTER(Stats)]),
         "ira_resident_start": (i32, [H, i32]),
+        "ira_l1ra_irls": (i32, [H, i64, i64, i32, pi32, pf64, i64, pf64, i64, i32, f64, i32, f64, i32, f64, pf64, pi32,
+                                pi32, pf64, C.POINTER(Stats)]),
         "ira_init_mst": (i32, [H, i64, i64, i32, pi32, pf64, i64, pf64, i64, C.POINTER(MstStats)]),
         "ira_init_mst_resident": (i32, [H, i32, C.POINTER(MstStats)]),
     }

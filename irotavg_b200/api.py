@@ -81,7 +81,7 @@ class Solver:
     def __init__(self, device: int = -1, cg_rtol: float | None = None, cg_max_iters: int | None = None,
                  cg_check_every: int | None = None, lanes_per_row: int = 0, world_size: int = 1,
                  rank: int = 0, profile: bool = False, solver: int = 0, spmv_variant: int = 0,
-                 pair_theta: float | None = None):
+                 pair_theta: float | None = None, small_path: bool = True):
         self._lib = _lib.load()
         opt = Options()
         self._check(self._lib.ira_options_default(C.byref(opt)), None)
@@ -100,6 +100,7 @@ class Solver:
         opt.spmv_variant = spmv_variant
         if pair_theta is not None:
             opt.pair_theta = pair_theta
+        opt.small_path = 0 if small_path else 1
         self.options = opt
         self._h = C.c_void_p()
         self._check(self._lib.ira_create(C.byref(self._h), C.byref(opt)), None)
@@ -203,6 +204,24 @@ class Solver:
     def resident_start(self, from_current: bool):
         """False: resident calls restart from the uploaded Q0; True: continue from the current device Q."""
         self._check(self._lib.ira_resident_start(self._h, 1 if from_current else 0), self._h)
+
+    # -- l1ra followed by irls on one upload (both callers' sequence) ---------------------------
+    def l1ra_irls(self, QQ, I, Q, f, l1_iters, l1_th, cost, sigma, irls_iters, irls_th):
+        """ira_l1ra_irls: src/ViewGraph.cpp:1402-1417 / ral/test.cpp:295-300.  Returns (Q, weights, l1_iters,
+        irls info)."""
+        QQf = _colmajor(QQ, 4)
+        Qf = np.array(_colmajor(Q, 4), order="F", copy=True)
+        Ip = _pairs(I)
+        m, n = QQf.shape[0], Qf.shape[0]
+        weights = np.zeros(m, dtype=np.float64)
+        l1o, iro = C.c_int32(0), C.c_int32(0)
+        runtime = C.c_double(0.0)
+        st = Stats()
+        self._check(self._lib.ira_l1ra_irls(self._h, m, n, int(f), _pi(Ip), _pd(QQf), max(m, 1), _pd(Qf), max(n, 1),
+                                            int(l1_iters), float(l1_th), int(cost), float(sigma), int(irls_iters),
+                                            float(irls_th), _pd(weights), C.byref(l1o), C.byref(iro), C.byref(runtime),
+                                            C.byref(st)), self._h)
+        return np.ascontiguousarray(Qf), weights, l1o.value, _info(st, iro.value, runtime.value)
 
     # -- irotavg::init_mst --------------------------------------------------------------------
     def init_mst(self, Q, QQ, I, f):

@@ -24,6 +24,7 @@
 #include "ira_pcg.cuh"
 #include "ira_l1ra.cuh"
 #include "ira_mst.cuh"
+#include "ira_small.cuh"
 
 using namespace ira;
 
@@ -96,6 +97,9 @@ struct ira_context {
   DevBuf pdX, pdATV, pdATDV, pdW1P, pdDX, diag3, dinv3, pdctl, pdtrial;
   PdCtl* h_pdctl = nullptr;  // pinned
   DevBuf mst_label, mst_label2, mst_order, mst_order2, mst_done, mst_ctl;   // init_mst (ira_mst.cuh)
+  unsigned char* small_in = nullptr;    // mapped pinned blocks of the single-block window solver (ira_small.cuh)
+  unsigned char* small_out = nullptr;
+  bool small_ready = false;
   int start_mode = 0;        // 0: resident calls restart from the uploaded Q0, 1: continue from the current Q
   int nslices = 0, npos = 0;
   int64_t sell_total = 0;
@@ -722,6 +726,8 @@ ira_status ira_destroy(ira_handle h) {
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->h_pdctl) cudaFreeHost(h->h_pdctl);
+  if (h->small_in) cudaFreeHost(h->small_in);
+  if (h->small_out) cudaFreeHost(h->small_out);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return IRA_OK;
@@ -1375,6 +1381,56 @@ ira_status ira_init_mst(ira_handle h, int64_t m, int64_t n_total, int32_t f_init
 // l1ra followed by irls on one upload: the call sequence of both callers
 // (ral/test.cpp:295-300, src/ViewGraph.cpp:1407-1417)
 // ---------------------------------------------------------------------------------------------
+namespace {
+// The window-sized call as one launch of one block; host buffers <-> mapped pinned blocks.
+ira_status small_l1ra_irls(ira_context* h, int m, int n, int f, const int32_t* I_pairs, const double* QQ, int64_t ld_qq,
+                           double* Q, int64_t ld_q, int l1_max, double l1_th, int cost, double sigma, int irls_max,
+                           double irls_th, double* weights, int32_t* l1_out, int32_t* irls_out, ira_stats* st) {
+  IRA_CUDA(h, cudaSetDevice(h->device));
+  if (!h->small_ready) {
+    IRA_CUDA(h, cudaHostAlloc((void**)&h->small_in, small_in_bytes(kSmM, kSmN), cudaHostAllocMapped));
+    IRA_CUDA(h, cudaHostAlloc((void**)&h->small_out, small_out_bytes(kSmM, kSmN), cudaHostAllocMapped));
+    IRA_CUDA(h, cudaFuncSetAttribute(k_small_l1ra_irls, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(SmallSmem)));
+    h->small_ready = true;
+  }
+  for (int k = 0; k < 2 * m; ++k)
+    if (I_pairs[k] < 0 || I_pairs[k] >= n) { h->err = "edge endpoint out of range [0, n_total)"; return IRA_ERR_INVALID_ARG; }
+  SmallIn hd;
+  memset(&hd, 0, sizeof hd);
+  hd.m = m; hd.n = n; hd.f = f; hd.cost = cost; hd.l1_max_iters = l1_max; hd.irls_max_iters = irls_max;
+  hd.l1_th = l1_th; hd.irls_th = irls_th; hd.sigma = sigma;
+  memcpy(h->small_in, &hd, sizeof hd);
+  memcpy(h->small_in + small_in_I(), I_pairs, sizeof(int32_t) * 2 * (size_t)m);
+  double* qq = reinterpret_cast<double*>(h->small_in + small_in_QQ(m));
+  double* q0 = reinterpret_cast<double*>(h->small_in + small_in_Q(m));
+  for (int c = 0; c < 4; ++c) {
+    memcpy(qq + (size_t)c * m, QQ + (size_t)c * ld_qq, sizeof(double) * (size_t)m);
+    memcpy(q0 + (size_t)c * n, Q + (size_t)c * ld_q, sizeof(double) * (size_t)n);
+  }
+  unsigned char *din = nullptr, *dout = nullptr;
+  IRA_CUDA(h, cudaHostGetDevicePointer((void**)&din, h->small_in, 0));
+  IRA_CUDA(h, cudaHostGetDevicePointer((void**)&dout, h->small_out, 0));
+  k_small_l1ra_irls<<<1, kSmThreads, sizeof(SmallSmem), h->stream>>>(din, dout);
+  IRA_TRY(launch_check(h, "k_small_l1ra_irls"));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  const SmallOut* oh = reinterpret_cast<const SmallOut*>(h->small_out);
+  const double* qo = reinterpret_cast<const double*>(h->small_out + sizeof(SmallOut));
+  for (int c = 0; c < 4; ++c) memcpy(Q + (size_t)c * ld_q, qo + (size_t)c * n, sizeof(double) * (size_t)n);
+  if (m > 0) memcpy(weights, qo + (size_t)4 * n, sizeof(double) * (size_t)m);
+  if (l1_out) *l1_out = oh->l1_iters;
+  if (irls_out) *irls_out = oh->irls_iters;
+  if (st) {
+    memset(st, 0, sizeof *st);
+    st->irls_iters = oh->irls_iters;
+    st->kernel_launches = 1;
+    for (int k = 0; k < std::min(oh->irls_iters, kSmScores); ++k) st->score[k] = oh->irls_score[k];
+  }
+  if (oh->nonfinite) { h->err = "score became non-finite"; return IRA_ERR_NONFINITE; }
+  return IRA_OK;
+}
+}  // namespace
+
 extern "C" ira_status ira_l1ra_irls(ira_handle h, int64_t m, int64_t n_total, int32_t f, const int32_t* I_pairs,
                                     const double* QQ, int64_t ld_qq, double* Q, int64_t ld_q, int32_t l1_max_iters,
                                     double l1_change_th, int32_t cost, double sigma, int32_t irls_max_iters,
@@ -1384,6 +1440,14 @@ extern "C" ira_status ira_l1ra_irls(ira_handle h, int64_t m, int64_t n_total, in
   IRA_TRY(check_args(h, m, n_total, f, I_pairs, QQ, ld_qq, Q, ld_q));
   if (m > 0 && !weights) { h->err = "null weights"; return IRA_ERR_INVALID_ARG; }
   if (cost < 0 || cost >= kNumCosts) { h->err = "Unknown cost!!"; return IRA_ERR_UNKNOWN_COST; }
+  if (h->opt.small_path == 0 && h->opt.world_size <= 1 && n_total <= kSmN && n_total - f >= 1 && n_total - f <= kSmNF &&
+      m <= kSmM) {
+    const ira_status rs = small_l1ra_irls(h, (int)m, (int)n_total, f, I_pairs, QQ, ld_qq, Q, ld_q, l1_max_iters,
+                                          l1_change_th, cost, sigma, irls_max_iters, irls_change_th, weights,
+                                          l1_iters_out, irls_iters_out, irls_stats);
+    if (runtime_s_out) *runtime_s_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return rs;
+  }
   IRA_TRY(ira_problem_upload(h, m, n_total, f, I_pairs, QQ, ld_qq, Q, ld_q));
   ira_status rc = ira_l1ra_resident(h, l1_max_iters, l1_change_th, l1_iters_out, nullptr, nullptr);
   if (rc != IRA_OK && rc != IRA_ERR_NONFINITE) return rc;
