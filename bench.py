@@ -172,7 +172,11 @@ def workload_config(args, world):
                     f"sigma_n=0.05 rad, 10% outliers, seed 20190319), {IRLS_ITERS} IRLS iters per step, cost {args.cost}, "
                     "sigma 5 deg, f=1",
         "cost": args.cost, "irls_iters_per_step": IRLS_ITERS, "cg_rtol": 1e-10,
-        "parallelism": "single GPU" if world == 1 else f"edges sharded over {world} ranks, NCCL all-reduce of node vectors",
+        "parallelism": "single GPU" if world == 1 else (
+            f"rows of A^T D^2 A partitioned over {world} ranks, one persistent PCG kernel per rank exchanging u slices / "
+            "dot products / barrier flags through NVLink peer memory (CUDA IPC); edge kernels replicated"
+            if getattr(args, "shard_mode", 0) == 1 else
+            f"edges sharded over {world} ranks, NCCL all-reduce of node vectors per PCG iteration"),
         "l2": "512 MB memset between timed steps flushes L2 (working set ~150 MB also exceeds the 126 MB L2)",
     }
 
@@ -199,14 +203,37 @@ def run_ours(args):
     cost = COSTS[args.cost]
     m, n, f = g.m, g.n, g.f
     from irotavg_b200.sharding import broadcast_unique_id, edge_shard
-    lo, hi = edge_shard(m, world, rank)                              # this rank's edge shard
-    I_loc = np.ascontiguousarray(g.I[lo:hi])
-    QQ_loc = np.asfortranarray(g.QQ[lo:hi])
-    m_loc = hi - lo
-
-    s = ira.Solver(device=local_rank, world_size=world, rank=rank)
-    if world > 1:
+    # N > 1: rows of the normal equations partitioned over the ranks, one persistent kernel per rank exchanging
+    # through NVLink peer memory (shard_mode 1, every rank holds the graph).  If CUDA IPC between the ranks is not
+    # available on the box, fall back - on all ranks together - to edge shards + NCCL all-reduce (shard_mode 0).
+    shard_mode = 1 if world > 1 and not args.nccl_allreduce else 0
+    s = None
+    while True:
+        if shard_mode == 1:
+            lo, hi = 0, m
+        else:
+            lo, hi = edge_shard(m, world, rank)                      # this rank's edge shard
+        I_loc = np.ascontiguousarray(g.I[lo:hi])
+        QQ_loc = np.asfortranarray(g.QQ[lo:hi])
+        m_loc = hi - lo
+        s = ira.Solver(device=local_rank, world_size=world, rank=rank, shard_mode=shard_mode)
+        if world == 1:
+            break
         s.comm_init(broadcast_unique_id(dist, ira.Solver, rank, device="cuda"))
+        bad = 0
+        if shard_mode == 1:
+            try:
+                s.upload(QQ_loc, I_loc, g.Q0, f)
+            except ira.IraError as e:
+                print(f"[bench] rank {rank}: peer-memory set-up failed: {e}", file=sys.stderr, flush=True)
+                bad = 1
+        t = torch.tensor([bad], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if int(t.item()) == 0:
+            break
+        s.close()
+        shard_mode = 0
+    args.shard_mode = shard_mode
     ext = torch.cuda.ExternalStream(s.stream_ptr, device=torch.device("cuda", local_rank))
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 
@@ -410,6 +437,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cost", default="L1", choices=sorted(COSTS))
+    ap.add_argument("--nccl-allreduce", action="store_true",
+                    help="N > 1: edge shards + NCCL all-reduce per PCG iteration instead of the peer-memory solve")
     ap.add_argument("--ref-iters", type=int, default=10, help="IRLS iterations in the CPU port's bounded sample")
     args = ap.parse_args()
     if args.impl == "reference":

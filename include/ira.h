@@ -74,7 +74,13 @@ typedef struct ira_options {
   int32_t small_path;      /* window-sized problems (n_total <= 64, 1 <= n_free <= 32, m <= 256) in
                               ira_l1ra_irls run as ONE single-block kernel with dense Cholesky solves
                               (irotavg_b200/csrc/ira_small.cuh): 0 = yes (default), 1 = never              */
-  int32_t reserved[4];
+  int32_t shard_mode;      /* world_size > 1 only.  0: every rank passes ITS EDGE SHARD; per-node partial sums are
+                              all-reduced with NCCL once per PCG iteration.  1: every rank passes the WHOLE graph;
+                              the rows of A^T D^2 A are partitioned over the ranks and ONE persistent kernel per
+                              rank runs the solve, exchanging vector slices / dot products / barrier flags by
+                              loads and stores into the peers' HBM over NVLink (CUDA IPC mappings,
+                              irotavg_b200/csrc/ira_peer.cuh); weights come back whole on every rank          */
+  int32_t reserved[3];
 } ira_options;
 
 #define IRA_STATS_MAX_ITERS 256
@@ -117,7 +123,7 @@ ira_status  ira_get_stream(ira_handle h, void** stream_out);
  * (ral/l1_irls.cpp:755-780) and is rebuilt on the device, including make_A's rule that an edge
  * whose second endpoint is fixed contributes nothing.  max_iters == 0 returns Q untouched.
  * With world_size > 1 every rank passes ITS edge shard (I, QQ, weights of m_local edges) and the
- * same full Q; Q comes back identical on all ranks. */
+ * same full Q (shard_mode 0), or the whole graph (shard_mode 1); Q comes back identical on all ranks. */
 ira_status ira_irls(ira_handle h, int64_t m, int64_t n_total, int32_t f,
                     const int32_t* I_pairs, const double* QQ, int64_t ld_qq,
                     double* Q, int64_t ld_q,

@@ -38,7 +38,8 @@ class Options(C.Structure):
         ("solver", C.c_int32),
         ("spmv_variant", C.c_int32),
         ("small_path", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("shard_mode", C.c_int32),
+        ("reserved", C.c_int32 * 3),
     ]
 
 

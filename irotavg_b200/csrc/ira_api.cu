@@ -25,6 +25,7 @@
 #include "ira_l1ra.cuh"
 #include "ira_mst.cuh"
 #include "ira_small.cuh"
+#include "ira_peer.cuh"
 
 using namespace ira;
 
@@ -55,6 +56,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load() {
@@ -65,9 +67,10 @@ struct NcclApi {
     GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
     CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
     AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
     CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
     GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-    return GetUniqueId && CommInitRank && AllReduce && CommDestroy && GetErrorString;
+    return GetUniqueId && CommInitRank && AllReduce && AllGather && CommDestroy && GetErrorString;
   }
 };
 NcclApi g_nccl;
@@ -112,6 +115,14 @@ struct ira_context {
 
   // comm
   ncclComm_t comm = nullptr;
+  // peer-memory solve (ira_peer.cuh): this rank's window, the peers' windows mapped through CUDA IPC
+  bool peer = false;
+  DevBuf peer_win, sell_pos, ipc_stage;
+  void* peer_mapped[kPeerMax] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void* peer_exported = nullptr;        // the window address the current mappings were exchanged for
+  int peer_n = 0;
+  unsigned long long peer_epoch = 0;
+  int peer_blocks_per_sm = 0;
 
   // profiling
   struct Span { int cls; cudaEvent_t a, b; };
@@ -398,7 +409,7 @@ ira_status run_pairing(ira_context* h) {
                                                      h->opt.pair_theta, h->pair_key.as<unsigned long long>(),
                                                      h->pair_w2.as<double>());
   IRA_TRY(launch_check(h, "k_pair_best"));
-  if (h->opt.world_size > 1) {        // a node's edges live on several ranks: global strongest pick
+  if (h->opt.world_size > 1 && !h->peer) {   // a node's edges live on several ranks: global strongest pick
     IRA_TRY(allreduce(h, h->pair_key.p, h->pair_key2.p, (size_t)h->n, ncclUint64, ncclMax));
     k_pair_select<<<grid_nodes(h, h->n), 256, 0, h->stream>>>(h->pair_key.as<unsigned long long>(),
                                                            h->pair_key2.as<unsigned long long>(), h->pair_w2.as<double>(), h->n);
@@ -459,6 +470,102 @@ ira_status solve_pcg_persistent(ira_context* h) {
   }
   IRA_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPcgThreads), args, 0, h->stream));
   h->launches++;
+  return IRA_OK;
+}
+
+// Map every rank's window into this process (CUDA IPC handles all-gathered over the NCCL communicator).
+ira_status peer_setup(ira_context* h) {
+  const int G = h->opt.world_size, n = std::max(h->n, 1);
+  if (G > kPeerMax) { h->err = "peer-memory solve supports at most 8 ranks"; return IRA_ERR_INVALID_ARG; }
+  if (!h->comm) { h->err = "world_size > 1 but ira_comm_init was not called"; return IRA_ERR_COMM; }
+  void* before = h->peer_win.p;
+  IRA_CUDA(h, h->peer_win.reserve(peer_window_bytes(n)));
+  IRA_CUDA(h, h->sell_pos.reserve(sizeof(int) * (size_t)n));
+  // every rank takes the same decision: all see the same n, and a window only ever grows
+  if (h->peer_win.p != before || h->peer_exported != h->peer_win.p) {
+    for (int g = 0; g < kPeerMax; ++g)
+      if (h->peer_mapped[g]) { cudaIpcCloseMemHandle(h->peer_mapped[g]); h->peer_mapped[g] = nullptr; }
+    IRA_CUDA(h, cudaMemsetAsync(h->peer_win.p, 0, h->peer_win.cap, h->stream));
+    cudaIpcMemHandle_t mine;
+    IRA_CUDA(h, cudaIpcGetMemHandle(&mine, h->peer_win.p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    IRA_CUDA(h, h->ipc_stage.reserve(64 * (size_t)(G + 1)));
+    unsigned char* st = h->ipc_stage.as<unsigned char>();
+    IRA_CUDA(h, cudaMemcpyAsync(st, &mine, 64, cudaMemcpyHostToDevice, h->stream));
+    ncclResult_t r = g_nccl.AllGather(st, st + 64, 64, ncclUint8, h->comm, h->stream);
+    if (r != ncclSuccess) { h->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(r); return IRA_ERR_COMM; }
+    std::vector<cudaIpcMemHandle_t> all((size_t)G);
+    IRA_CUDA(h, cudaMemcpyAsync(all.data(), st + 64, 64 * (size_t)G, cudaMemcpyDeviceToHost, h->stream));
+    IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int g = 0; g < G; ++g) {
+      if (g == h->opt.rank) continue;
+      cudaError_t e = cudaIpcOpenMemHandle(&h->peer_mapped[g], all[(size_t)g], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        h->err = std::string("cudaIpcOpenMemHandle failed (peer-memory solve needs CUDA IPC between the ranks): ") +
+                 cudaGetErrorString(e);
+        return IRA_ERR_COMM;
+      }
+    }
+    h->peer_exported = h->peer_win.p;
+    h->peer_epoch = 0;
+    // nobody may start a solve (and write into a peer's window) before every rank has zeroed its flags
+    IRA_CUDA(h, cudaMemsetAsync(st, 0, 8, h->stream));
+    r = g_nccl.AllReduce(st, st, 1, ncclFloat64, ncclSum, h->comm, h->stream);
+    if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r); return IRA_ERR_COMM; }
+    IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  h->peer_n = n;
+  k_sell_inverse<<<cdiv(h->npos, 256), 256, 0, h->stream>>>(h->sell_row.as<int>(), h->npos, h->sell_pos.as<int>());
+  IRA_TRY(launch_check(h, "k_sell_inverse"));
+  if (h->peer_blocks_per_sm == 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_peer<0, 4>, kPcgThreads, 0) != cudaSuccess || nb < 1) {
+      cudaGetLastError();
+      h->err = "k_pcg_peer cannot be launched cooperatively on this device";
+      return IRA_ERR_CUDA;
+    }
+    h->peer_blocks_per_sm = nb;
+  }
+  return IRA_OK;
+}
+
+// One linear step, rows partitioned over the ranks, exchanged through peer memory (ira_peer.cuh).
+ira_status solve_pcg_peer(ira_context* h) {
+  IRA_TRY(run_rhs(h));                                   // replicated: every rank holds the whole graph
+  const bool pairing = h->opt.pair_theta > 0.0;
+  if (pairing) IRA_TRY(run_pairing(h));
+  PcgPeerParams q;
+  memset(&q, 0, sizeof q);
+  PcgParams& pp = q.base;
+  pp.mate = pairing ? h->mate.as<int>() : nullptr;
+  pp.pc1 = pairing ? h->pc1.as<double>() : nullptr;
+  pp.pc2 = pairing ? h->pc2.as<double>() : nullptr;
+  pp.npairs = pairing ? h->npairs.as<int>() : nullptr;
+  pp.n = h->peer_n; pp.nslices = h->nslices; pp.max_iters = std::max(0, h->opt.cg_max_iters);
+  pp.rtol2 = h->opt.cg_rtol * h->opt.cg_rtol;
+  pp.sell_row = h->sell_row.as<int>(); pp.slice_off = h->slice_off.as<int>(); pp.slice_width = h->slice_width.as<int>();
+  pp.sell_col = h->sell_col.as<int>(); pp.sell_w2 = h->sell_w2.as<double>();
+  pp.B = h->B.as<double4>(); pp.diag = h->diag.as<double>();
+  pp.X = nullptr; pp.R = h->R.as<double4>(); pp.U = nullptr; pp.W = h->AP.as<double4>();
+  pp.P = h->P.as<double4>(); pp.S = h->S.as<double4>();
+  pp.dinv = h->dinv.as<double>(); pp.partials = h->partials.as<double>(); pp.ctl = h->ctl.as<Ctl>();
+  const int G = h->opt.world_size;
+  q.world = G; q.rank = h->opt.rank;
+  for (int g = 0; g <= kPeerMax; ++g) q.slice_bound[g] = (int)(((int64_t)h->nslices * std::min(g, G)) / G);
+  q.slice_lo = q.slice_bound[q.rank]; q.slice_hi = q.slice_bound[q.rank + 1];
+  q.sell_pos = h->sell_pos.as<int>();
+  for (int g = 0; g < G; ++g) q.win[g] = (unsigned char*)(g == q.rank ? h->peer_win.p : h->peer_mapped[g]);
+  q.epoch_base = h->peer_epoch;
+  const int own = std::max(1, q.slice_hi - q.slice_lo);
+  const int grid = std::max(1, std::min(own, h->sms * h->peer_blocks_per_sm));
+  ProfScope ps(h, KC_PCG);
+  void* args[] = {(void*)&q};
+  void* fn = h->opt.spmv_variant == 1 ? (void*)k_pcg_peer<1, 4> : (void*)k_pcg_peer<0, 4>;
+  IRA_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPcgThreads), args, 0, h->stream));
+  h->launches++;
+  const PeerWindow me = peer_window_at((unsigned char*)h->peer_win.p, h->peer_n);
+  IRA_CUDA(h, cudaMemcpyAsync(h->X.p, me.X, sizeof(double4) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
   return IRA_OK;
 }
 
@@ -713,6 +820,9 @@ ira_status ira_destroy(ira_handle h) {
   if (!h) return IRA_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int g = 0; g < kPeerMax; ++g)
+    if (h->peer_mapped[g]) { cudaIpcCloseMemHandle(h->peer_mapped[g]); h->peer_mapped[g] = nullptr; }
+  h->peer_win.release();
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (DevBuf* b : {&h->I, &h->QQ, &h->weights, &h->wres, &h->Q, &h->Q0, &h->stage, &h->rowptr, &h->ent_col,
                     &h->ent_eid, &h->ent_w2, &h->keys, &h->vals, &h->cubtmp, &h->X, &h->R, &h->Z, &h->P,
@@ -721,7 +831,7 @@ ira_status ira_destroy(ira_handle h) {
                     &h->R2, &h->S2, &h->pdU, &h->pdAX, &h->pdL1, &h->pdL2, &h->pdADX, &h->pdDU, &h->pdDL1, &h->pdDL2, &h->pdEV,
                     &h->pdSIGX, &h->sell_w3, &h->pdX, &h->pdATV, &h->pdATDV, &h->pdW1P, &h->pdDX, &h->diag3, &h->dinv3,
                     &h->pdctl, &h->pdtrial, &h->mst_label, &h->mst_label2, &h->mst_order, &h->mst_order2, &h->mst_done,
-                    &h->mst_ctl, &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs})
+                    &h->mst_ctl, &h->sell_pos, &h->ipc_stage, &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs})
     b->release();
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -758,6 +868,12 @@ ira_status ira_problem_upload(ira_handle h, int64_t m, int64_t n_total, int32_t 
     if (h->sell_total > 3ll * std::max(h->nnz, 1) + 64ll * kSellSigma) h->fmt_csr = true;
   }
   h->persistent = !h->fmt_csr && h->opt.world_size <= 1 && (h->opt.solver & 3) != 1 && h->pcg_blocks_per_sm > 0;
+  h->peer = false;
+  if (h->opt.world_size > 1 && h->opt.shard_mode == 1) {
+    if (h->fmt_csr || h->pcg_blocks_per_sm <= 0) { h->err = "peer-memory solve needs the SELL pattern and cooperative launch"; return IRA_ERR_INVALID_ARG; }
+    IRA_TRY(peer_setup(h));
+    h->peer = true;
+  }
   h->prev_cg = 0;
   h->uploaded = true;
   h->start_mode = 0;
@@ -807,7 +923,8 @@ ira_status ira_irls_resident(ira_handle h, int32_t cost, double sigma, int32_t m
     IRA_TRY(run_residual(h, h->Q.as<double4>(), 0));                       // :592-593
     int cg_it = 0, hit = 0;
     double rel = 0.0;
-    if (h->persistent) IRA_TRY(solve_pcg_persistent(h));                   // :596-612
+    if (h->peer) IRA_TRY(solve_pcg_peer(h));
+    else if (h->persistent) IRA_TRY(solve_pcg_persistent(h));              // :596-612
     else IRA_TRY(solve_pcg(h, &cg_it, &rel, &hit));
     if (m > 0) {
       ProfScope ps(h, KC_WEIGHTS);
@@ -824,7 +941,8 @@ ira_status ira_irls_resident(ira_handle h, int32_t cost, double sigma, int32_t m
     }
     IRA_TRY(fetch_ctl(h));
     score = h->h_ctl->score;
-    if (h->persistent) {
+    if (h->peer) h->peer_epoch = h->h_ctl->epoch;
+    if (h->persistent || h->peer) {
       const Ctl& c = *h->h_ctl;
       cg_it = c.cg_iters;
       bool conv = true;
@@ -857,7 +975,7 @@ ira_status ira_irls_resident(ira_handle h, int32_t cost, double sigma, int32_t m
     stats->t_total_ms = ms;
     stats->kernel_launches = h->launches - launches0;
     const Ctl& c = *h->h_ctl;
-    if (h->persistent && c.cyc_total > 0) {          // block 0's phase clocks -> milliseconds
+    if ((h->persistent || h->peer) && c.cyc_total > 0) {          // block 0's phase clocks -> milliseconds
       const double ms_per_cycle = 1e-6 * (double)c.ns_total / (double)c.cyc_total;
       stats->pcg_spmv_ms = ms_per_cycle * (double)c.cyc_spmv;
       stats->pcg_update_ms = ms_per_cycle * (double)c.cyc_update;

@@ -91,6 +91,7 @@ struct Ctl {
   // persistent solve only: SM-clock cycles block 0 spent in the SpMV+reduce and update phases,
   // whole-kernel cycles and globaltimer nanoseconds (to convert cycles to time), SpMV phases run
   long long cyc_spmv, cyc_update, cyc_total, ns_total, pcg_spmv_phases;
+  unsigned long long epoch;   // peer-memory solve (ira_peer.cuh): last cross-GPU barrier epoch used
 };
 
 constexpr int kRedMaxBlocks = 1184;      // 148 SMs x 8: upper bound on reduction grids

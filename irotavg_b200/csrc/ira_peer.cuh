@@ -1,0 +1,319 @@
+// Multi-GPU linear solve over NVLink peer memory: ONE persistent cooperative kernel per rank runs the whole
+// PCG solve; the ranks exchange vector slices, dot products and barrier flags by plain loads / stores into
+// each other's HBM (one process per GPU, buffers mapped with CUDA IPC).  No NCCL call inside the solve.
+//
+// Partition.  The rows of A^T D^2 A (SELL slices, ira_pcg.cuh) are split into `world` contiguous slice ranges;
+// rank g owns the rows of its range, i.e. walks the adjacency (the edge list) of its nodes only.  Every rank
+// holds the whole graph and runs the O(m) edge kernels (residual, weights, rhs) redundantly - 3 % of the time
+// at one GPU - so the only data that must cross GPUs is what the PCG iteration itself produces:
+//   (1) after the SpMV: 9 partial dot products per rank (gamma = r.u, delta = u.Au, |r|^2 for 3 right-hand
+//       sides) -> written into every peer's slot array, summed by everybody in rank order (bitwise identical
+//       on all ranks, so alpha / beta / the stopping decision agree without a broadcast);
+//   (2) after the vector update: the owner writes its rows of the new u = M^-1 r into EVERY rank's copy of u
+//       (an all-gather by direct P2P stores, fused into the update loop - the transfer of row i overlaps the
+//       arithmetic of row i+1), and, for rows of 2x2 preconditioner blocks whose mate lives on another rank,
+//       its (r, s) and w to the mate's owner only.
+// Cross-GPU barrier = local grid barrier, then block 0 stores an epoch number into every peer's flag array
+// (after a system-scope fence), then every block polls its own rank's flags: 2 per PCG iteration.
+// Chronopoulos-Gear recurrences as in k_pcg_persistent (same arithmetic per row).
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ira_pcg.cuh"
+
+namespace ira {
+
+constexpr int kPeerMax = 8;
+
+// Layout of the per-rank window (one cudaMalloc, exported with cudaIpcGetMemHandle).
+struct PeerWindow {
+  double4* U;        // [n]  full search-direction input vector u = M^-1 r (every owner writes its rows)
+  double4* X;        // [n]  solution, all-gathered at the end of the solve
+  double4* MR[2];    // [n]  ping-pong (r, s) of paired rows, written by the row's owner into the MATE's owner
+  double4* MS[2];
+  double4* MW;       // [n]  w = A u of paired rows, same routing
+  double* dots;      // [2][kPeerMax][16]
+  unsigned long long* flags;   // [kPeerMax]
+};
+__host__ __device__ inline size_t peer_window_bytes(int n) {
+  return (size_t)7 * n * sizeof(double4) + 2 * kPeerMax * 16 * sizeof(double) + kPeerMax * sizeof(unsigned long long) + 256;
+}
+__host__ __device__ inline PeerWindow peer_window_at(unsigned char* base, int n) {
+  PeerWindow w;
+  double4* v = reinterpret_cast<double4*>(base);
+  w.U = v; w.X = v + (size_t)n; w.MR[0] = v + (size_t)2 * n; w.MR[1] = v + (size_t)3 * n;
+  w.MS[0] = v + (size_t)4 * n; w.MS[1] = v + (size_t)5 * n; w.MW = v + (size_t)6 * n;
+  w.dots = reinterpret_cast<double*>(v + (size_t)7 * n);
+  w.flags = reinterpret_cast<unsigned long long*>(w.dots + 2 * kPeerMax * 16);
+  return w;
+}
+
+struct PcgPeerParams {
+  PcgParams base;              // X of base is unused (the window's X is the output)
+  int world, rank;
+  int slice_lo, slice_hi;      // this rank's slices
+  const int* sell_pos;         // row -> SELL position (owner of a row = rank whose slice range holds it)
+  int slice_bound[kPeerMax + 1];
+  unsigned char* win[kPeerMax];   // window base of every rank in THIS process's address space (own: local)
+  unsigned long long epoch_base;  // flags hold monotonically increasing epochs across launches
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// All blocks of all ranks pass this point together.  Every thread's earlier remote stores are made visible
+// system-wide first (fence), the local grid barrier collects them, block 0 then raises this rank's epoch in
+// every rank's flag array, and every block waits until all ranks have raised theirs.
+__device__ __forceinline__ void peer_barrier(const PcgPeerParams& q, cooperative_groups::grid_group& grid,
+                                             unsigned long long epoch) {
+  // one system-scope fence per block: after the block barrier thread 0 has (transitively) observed every store
+  // of its block, and the fence is cumulative - 148 fences per barrier instead of 113 664
+  __syncthreads();
+  if (threadIdx.x == 0) __threadfence_system();
+  grid.sync();
+  if (blockIdx.x == 0 && threadIdx.x < q.world) {
+    PeerWindow w = peer_window_at(q.win[threadIdx.x], q.base.n);
+    st_release_sys(w.flags + q.rank, epoch);
+  }
+  if (threadIdx.x < q.world) {
+    PeerWindow mine = peer_window_at(q.win[q.rank], q.base.n);
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
+    while (ld_relaxed_sys_u64(mine.flags + threadIdx.x) < epoch) {
+      if ((++spins & 0xfffu) == 0u) {                      // a peer that died must not hang this GPU for ever
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 20000000000ull) asm volatile("trap;");
+      }
+    }
+    __threadfence_system();                                // acquire: the peers' data stores precede their flags
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int peer_owner(const PcgPeerParams& q, int row) {
+  const int s = q.sell_pos[row] / kSellC;
+  int g = 0;
+#pragma unroll
+  for (int k = 1; k < kPeerMax; ++k) g += (k < q.world && s >= q.slice_bound[k]) ? 1 : 0;
+  return g;
+}
+
+template <int V, int UNR>
+__global__ void __launch_bounds__(kPcgThreads, 1)
+k_pcg_peer(const PcgPeerParams q) {
+  namespace cgx = cooperative_groups;
+  const PcgParams& p = q.base;
+  cgx::grid_group grid = cgx::this_grid();
+  __shared__ double red[kPcgNV * 32];
+  __shared__ double tot[kPcgNV];
+  __shared__ double sc_bb[3], sc_go[3], sc_ao[3], sc_a[3], sc_b[3], sc_rr[3];
+  __shared__ int sc_stop;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = blockIdx.x + gridDim.x * (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const PeerWindow me = peer_window_at(q.win[q.rank], p.n);
+  const bool has_pairs = p.npairs != nullptr && *p.npairs > 0;
+  unsigned long long epoch = q.epoch_base;
+  double v[kPcgNV];
+
+  // ---- start (replicated, local): u = M^-1 b for ALL rows, "previous" (r, s) = (b, 0) of paired rows;
+  //      own rows: x = 0, r = b, p = s = 0.  |b|^2 over all rows is the same number on every rank.
+#pragma unroll
+  for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
+  for (int s = gwarp; s < p.nslices; s += nwarps) {
+    const int row = p.sell_row[s * kSellC + lane];
+    if (row >= 0) {
+      const double4 b = ldg256(p.B + row);
+      const double d = p.diag[row];
+      const double di = p.pc1 ? p.pc1[row] : (d > 0.0 ? 1.0 / d : 0.0);
+      double4 u0 = make_double4(di * b.x, di * b.y, di * b.z, 0.0);
+      if (has_pairs) {
+        const int mt = p.mate[row];
+        if (mt >= 0) {
+          const double4 bm = ldg256(p.B + mt);
+          const double c2 = p.pc2[row];
+          u0.x += c2 * bm.x; u0.y += c2 * bm.y; u0.z += c2 * bm.z;
+          st256(me.MR[1] + row, b);
+          st256(me.MS[1] + row, make_double4(0, 0, 0, 0));
+        }
+      }
+      st256(me.U + row, u0);
+      if (s >= q.slice_lo && s < q.slice_hi) {
+        p.dinv[row] = di;
+        const double4 z4 = make_double4(0, 0, 0, 0);
+        st256(p.R + row, b); st256(p.P + row, z4); st256(p.S + row, z4); st256(me.X + row, z4);
+      }
+      v[0] += b.x * b.x; v[1] += b.y * b.y; v[2] += b.z * b.z;
+    }
+  }
+  pcg_grid_reduce(v, p.partials, grid, red, tot);
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < 3; ++c) { sc_bb[c] = v[c]; sc_rr[c] = v[c]; sc_go[c] = 1.0; sc_ao[c] = 1.0; }
+    sc_stop = !(v[0] > 0.0 || v[1] > 0.0 || v[2] > 0.0);
+  }
+  __syncthreads();
+  // nobody may write into a window before its owner finished initialising it
+  peer_barrier(q, grid, ++epoch);
+  int it = 0;
+  const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+  long long c_spmv = 0, c_upd = 0, c_mark = 0, c_begin = 0;
+  unsigned long long ns_begin = 0;
+  if (timer) { c_begin = c_mark = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_begin)); }
+
+  while (!sc_stop) {
+    // ---- phase A: w = A u on my rows, partial dots ----------------------------------------------
+#pragma unroll
+    for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
+    for (int s = q.slice_lo + gwarp; s < q.slice_hi; s += nwarps) {
+      const int row = p.sell_row[s * kSellC + lane];
+      const int width = p.slice_width[s];
+      const int64_t base = (int64_t)p.slice_off[s] + lane;
+      const double4 u = row >= 0 ? ld256(me.U + row) : make_double4(0, 0, 0, 0);
+      double ax, ay, az;
+      sell_row_apply<V, UNR>(p.sell_col, p.sell_w2, me.U, base, width, u, ax, ay, az);
+      if (row >= 0) {
+        const double4 w4 = make_double4(ax, ay, az, 0.0);
+        st256(p.W + row, w4);
+        if (has_pairs) {
+          const int mt = p.mate[row];
+          if (mt >= 0) st256(peer_window_at(q.win[peer_owner(q, mt)], p.n).MW + row, w4);   // the mate needs my w
+        }
+        const double4 r = ld256(p.R + row);
+        v[0] += r.x * u.x; v[1] += r.y * u.y; v[2] += r.z * u.z;
+        v[3] += u.x * ax;  v[4] += u.y * ay;  v[5] += u.z * az;
+        v[6] += r.x * r.x; v[7] += r.y * r.y; v[8] += r.z * r.z;
+      }
+    }
+    // rank-local block-ordered sum (pcg_grid_reduce contains one grid barrier) ...
+    pcg_grid_reduce(v, p.partials, grid, red, tot);
+    // ... then the rank totals go to every rank's slot array, and everybody adds the slots in rank order
+    const int par = it & 1;
+    if (blockIdx.x == 0 && threadIdx.x < q.world * kPcgNV) {
+      const int g = threadIdx.x / kPcgNV, k = threadIdx.x % kPcgNV;
+      peer_window_at(q.win[g], p.n).dots[(par * kPeerMax + q.rank) * 16 + k] = v[k];
+    }
+    peer_barrier(q, grid, ++epoch);
+    if (threadIdx.x < kPcgNV) {
+      double t = 0.0;
+      for (int g = 0; g < q.world; ++g) t += ld_relaxed_sys_f64(me.dots + (par * kPeerMax + g) * 16 + threadIdx.x);
+      tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kPcgNV; ++k) v[k] = tot[k];
+    if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; }
+    if (threadIdx.x == 0) {
+      bool conv = true;
+      for (int c = 0; c < 3; ++c) {
+        sc_rr[c] = v[6 + c];
+        if (!(v[6 + c] <= p.rtol2 * sc_bb[c])) conv = false;
+      }
+      if (conv || it >= p.max_iters) {
+        sc_stop = 1;
+      } else {
+        for (int c = 0; c < 3; ++c) {
+          const double gam = v[c], del = v[3 + c];
+          double beta = 0.0, den = del;
+          if (it > 0) {
+            beta = sc_go[c] > 0.0 ? gam / sc_go[c] : 0.0;
+            if (sc_ao[c] != 0.0) den = del - beta * gam / sc_ao[c];
+          }
+          const double alpha = den > 0.0 ? gam / den : 0.0;
+          sc_go[c] = gam; sc_ao[c] = alpha; sc_a[c] = alpha; sc_b[c] = beta;
+        }
+      }
+    }
+    __syncthreads();
+    if (sc_stop) break;
+    const double a0 = sc_a[0], a1 = sc_a[1], a2 = sc_a[2], b0 = sc_b[0], b1 = sc_b[1], b2 = sc_b[2];
+    // ---- phase B: my rows of p, s, x, r, u; u goes to every rank, (r, s) of paired rows to the mate's owner ----
+    const int cur = it & 1, old = cur ^ 1;
+    for (int s = q.slice_lo + gwarp; s < q.slice_hi; s += nwarps) {
+      const int row = p.sell_row[s * kSellC + lane];
+      if (row >= 0) {
+        const double4 u = ld256(me.U + row), w = ld256(p.W + row);
+        double4 pp = ld256(p.P + row), ss = ld256(p.S + row);
+        pp.x = u.x + b0 * pp.x; pp.y = u.y + b1 * pp.y; pp.z = u.z + b2 * pp.z;
+        ss.x = w.x + b0 * ss.x; ss.y = w.y + b1 * ss.y; ss.z = w.z + b2 * ss.z;
+        st256(p.P + row, pp); st256(p.S + row, ss);
+        double4 x = ld256(me.X + row), r = ld256(p.R + row);
+        const double di = p.dinv[row];
+        x.x += a0 * pp.x; x.y += a1 * pp.y; x.z += a2 * pp.z;
+        r.x -= a0 * ss.x; r.y -= a1 * ss.y; r.z -= a2 * ss.z;
+        st256(me.X + row, x); st256(p.R + row, r);
+        double4 un = make_double4(di * r.x, di * r.y, di * r.z, 0.0);
+        if (has_pairs) {
+          const int mt = p.mate[row];
+          if (mt >= 0) {
+            // the mate's new residual from its previous (r, s) and this iteration's w - all delivered before
+            // the dot-product barrier
+            const double4 rm = ld256(me.MR[old] + mt), sm = ld256(me.MS[old] + mt), wm = ld256(me.MW + mt);
+            const double c2 = p.pc2[row];
+            const double sm0 = wm.x + b0 * sm.x, sm1 = wm.y + b1 * sm.y, sm2 = wm.z + b2 * sm.z;
+            un.x += c2 * (rm.x - a0 * sm0); un.y += c2 * (rm.y - a1 * sm1); un.z += c2 * (rm.z - a2 * sm2);
+            const PeerWindow mw = peer_window_at(q.win[peer_owner(q, mt)], p.n);
+            st256(mw.MR[cur] + row, r);
+            st256(mw.MS[cur] + row, ss);
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < kPeerMax; ++g)
+          if (g < q.world) st256(reinterpret_cast<double4*>(q.win[g]) + row, un);       // window offset 0 = U
+      }
+    }
+    ++it;
+    peer_barrier(q, grid, ++epoch);
+    if (timer) { const long long c = clock64(); c_upd += c - c_mark; c_mark = c; }
+  }
+  // ---- all-gather of the solution: my rows of X into every other rank's window -------------------------
+  for (int s = q.slice_lo + gwarp; s < q.slice_hi; s += nwarps) {
+    const int row = p.sell_row[s * kSellC + lane];
+    if (row >= 0) {
+      const double4 x = ld256(me.X + row);
+      for (int g = 0; g < q.world; ++g)
+        if (g != q.rank) st256(peer_window_at(q.win[g], p.n).X + row, x);
+    }
+  }
+  peer_barrier(q, grid, ++epoch);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    p.ctl->epoch = epoch;
+    p.ctl->cg_iters = it;
+    for (int c = 0; c < 3; ++c) { p.ctl->bnorm2[c] = sc_bb[c]; p.ctl->rnorm2[c] = sc_rr[c]; }
+    p.ctl->done = 1;
+    unsigned long long ns_end;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_end));
+    p.ctl->cyc_spmv += c_spmv;
+    p.ctl->cyc_update += c_upd;
+    p.ctl->cyc_total += clock64() - c_begin;
+    p.ctl->ns_total += (long long)(ns_end - ns_begin);
+    p.ctl->pcg_spmv_phases += c_spmv > 0 ? it + 1 : 0;
+  }
+}
+
+// row -> SELL position
+__global__ void k_sell_inverse(const int* __restrict__ sell_row, int npos, int* __restrict__ sell_pos) {
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos < npos) { const int r = sell_row[pos]; if (r >= 0) sell_pos[r] = pos; }
+}
+
+}  // namespace ira
