@@ -81,6 +81,9 @@ typedef struct ira_options {
                               loads and stores into the peers' HBM over NVLink (CUDA IPC mappings,
                               irotavg_b200/csrc/ira_peer.cuh); weights come back whole on every rank          */
   int32_t reserved[3];
+  double  pair_theta3;     /* a still-single node joins the pair holding its strongest neighbour when that edge's
+                              normalised strength is >= pair_theta3 (3x3 blocks, inverted exactly); 0 = pairs only.
+                              Default 0.05                                                                      */
 } ira_options;
 
 #define IRA_STATS_MAX_ITERS 256

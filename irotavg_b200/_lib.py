@@ -40,6 +40,7 @@ class Options(C.Structure):
         ("small_path", C.c_int32),
         ("shard_mode", C.c_int32),
         ("reserved", C.c_int32 * 3),
+        ("pair_theta3", C.c_double),
     ]
 
 

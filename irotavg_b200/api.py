@@ -81,7 +81,8 @@ class Solver:
     def __init__(self, device: int = -1, cg_rtol: float | None = None, cg_max_iters: int | None = None,
                  cg_check_every: int | None = None, lanes_per_row: int = 0, world_size: int = 1,
                  rank: int = 0, profile: bool = False, solver: int = 0, spmv_variant: int = 0,
-                 pair_theta: float | None = None, small_path: bool = True, shard_mode: int = 0):
+                 pair_theta: float | None = None, small_path: bool = True, shard_mode: int = 0,
+                 pair_theta3: float | None = None):
         self._lib = _lib.load()
         opt = Options()
         self._check(self._lib.ira_options_default(C.byref(opt)), None)
@@ -102,6 +103,8 @@ class Solver:
             opt.pair_theta = pair_theta
         opt.small_path = 0 if small_path else 1
         opt.shard_mode = shard_mode
+        if pair_theta3 is not None:
+            opt.pair_theta3 = pair_theta3
         self.options = opt
         self._h = C.c_void_p()
         self._check(self._lib.ira_create(C.byref(self._h), C.byref(opt)), None)

@@ -94,7 +94,7 @@ struct ira_context {
   DevBuf X, R, Z, P, AP, B, diag, dinv, S, R2, S2;
   // SELL-32-sigma copy of the pattern (ira_pcg.cuh)
   DevBuf sell_row, slice_off, slice_width, slice_cnt, sell_col, sell_eid, sell_w2;
-  DevBuf pair_key, pair_key2, pair_w2, mate, pc1, pc2, npairs;
+  DevBuf pair_key, pair_key2, pair_w2, mate, pc1, pc2, npairs, mate2, pc3, att_key;
   // l1ra (ira_l1ra.cuh): per-edge / per-node primal-dual state, allocated on first use
   DevBuf pdU, pdAX, pdL1, pdL2, pdADX, pdDU, pdDL1, pdDL2, pdEV, pdSIGX, sell_w3;
   DevBuf pdX, pdATV, pdATDV, pdW1P, pdDX, diag3, dinv3, pdctl, pdtrial;
@@ -353,7 +353,7 @@ ira_status run_cg_init(ira_context* h) {
       h->B.as<double4>(), h->diag.as<double>(), h->dinv.as<double>(), h->X.as<double4>(),
       h->R.as<double4>(), h->Z.as<double4>(), h->P.as<double4>(), h->n, h->ctl.as<Ctl>(),
       h->partials.as<double>(), h->pairing ? h->mate.as<int>() : nullptr, h->pairing ? h->pc1.as<double>() : nullptr,
-      h->pairing ? h->pc2.as<double>() : nullptr);
+      h->pairing ? h->pc2.as<double>() : nullptr, h->mate2.as<int>(), h->pc3.as<double>());
   return launch_check(h, "k_cg_init");
 }
 
@@ -377,7 +377,7 @@ ira_status run_cg_iteration(ira_context* h) {
     if (h->pairing) {
       k_cg_precond<<<grid_nodes(h, h->n, kRedThreads), kRedThreads, 0, h->stream>>>(
           h->R.as<double4>(), h->Z.as<double4>(), h->mate.as<int>(), h->pc1.as<double>(), h->pc2.as<double>(), h->n,
-          h->ctl.as<Ctl>(), h->partials.as<double>());
+          h->ctl.as<Ctl>(), h->partials.as<double>(), h->mate2.as<int>(), h->pc3.as<double>());
       IRA_TRY(launch_check(h, "k_cg_precond"));
     }
   }
@@ -420,8 +420,26 @@ ira_status run_pairing(ira_context* h) {
   }
   k_pair_mate<<<grid_nodes(h, h->n), 256, 0, h->stream>>>(h->pair_key.as<unsigned long long>(), h->pair_w2.as<double>(),
                                                          h->diag.as<double>(), h->n, h->mate.as<int>(),
-                                                         h->pc1.as<double>(), h->pc2.as<double>(), h->npairs.as<int>());
-  return launch_check(h, "k_pair_mate");
+                                                         h->pc1.as<double>(), h->pc2.as<double>(), h->npairs.as<int>(),
+                                                         h->mate2.as<int>(), h->pc3.as<double>());
+  IRA_TRY(launch_check(h, "k_pair_mate"));
+  // third members (3x3 blocks); the edge-sharded NCCL path would need two more all-reduces per solve: pairs only
+  if (h->opt.pair_theta3 > 0.0 && (h->opt.world_size <= 1 || h->peer)) {
+    IRA_CUDA(h, cudaMemsetAsync(h->att_key.p, 0, sizeof(unsigned long long) * (size_t)h->n, h->stream));
+    k_attach_best<<<grid_slices(h), 256, 0, h->stream>>>(h->sell_row.as<int>(), h->slice_off.as<int>(),
+                                                       h->slice_width.as<int>(), h->sell_col.as<int>(),
+                                                       h->sell_w2.as<double>(), h->diag.as<double>(), h->mate.as<int>(),
+                                                       h->nslices, h->opt.pair_theta3, h->att_key.as<unsigned long long>());
+    IRA_TRY(launch_check(h, "k_attach_best"));
+    k_attach_block<<<grid_nodes(h, h->n), 256, 0, h->stream>>>(h->att_key.as<unsigned long long>(), h->sell_pos.as<int>(),
+                                                              h->slice_off.as<int>(), h->slice_width.as<int>(),
+                                                              h->sell_col.as<int>(), h->sell_w2.as<double>(),
+                                                              h->diag.as<double>(), h->pair_w2.as<double>(), h->n,
+                                                              h->mate.as<int>(), h->mate2.as<int>(), h->pc1.as<double>(),
+                                                              h->pc2.as<double>(), h->pc3.as<double>());
+    IRA_TRY(launch_check(h, "k_attach_block"));
+  }
+  return IRA_OK;
 }
 
 ira_status solve_pcg_persistent(ira_context* h) {
@@ -433,6 +451,8 @@ ira_status solve_pcg_persistent(ira_context* h) {
   pp.pc1 = pairing ? h->pc1.as<double>() : nullptr;
   pp.pc2 = pairing ? h->pc2.as<double>() : nullptr;
   pp.npairs = pairing ? h->npairs.as<int>() : nullptr;
+  pp.mate2 = pairing ? h->mate2.as<int>() : nullptr;
+  pp.pc3 = pairing ? h->pc3.as<double>() : nullptr;
   pp.n = h->n; pp.nslices = h->nslices; pp.max_iters = std::max(0, h->opt.cg_max_iters);
   pp.rtol2 = h->opt.cg_rtol * h->opt.cg_rtol;
   pp.sell_row = h->sell_row.as<int>(); pp.slice_off = h->slice_off.as<int>(); pp.slice_width = h->slice_width.as<int>();
@@ -480,7 +500,6 @@ ira_status peer_setup(ira_context* h) {
   if (!h->comm) { h->err = "world_size > 1 but ira_comm_init was not called"; return IRA_ERR_COMM; }
   void* before = h->peer_win.p;
   IRA_CUDA(h, h->peer_win.reserve(peer_window_bytes(n)));
-  IRA_CUDA(h, h->sell_pos.reserve(sizeof(int) * (size_t)n));
   // every rank takes the same decision: all see the same n, and a window only ever grows
   if (h->peer_win.p != before || h->peer_exported != h->peer_win.p) {
     for (int g = 0; g < kPeerMax; ++g)
@@ -516,8 +535,6 @@ ira_status peer_setup(ira_context* h) {
     IRA_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   h->peer_n = n;
-  k_sell_inverse<<<cdiv(h->npos, 256), 256, 0, h->stream>>>(h->sell_row.as<int>(), h->npos, h->sell_pos.as<int>());
-  IRA_TRY(launch_check(h, "k_sell_inverse"));
   if (h->peer_blocks_per_sm == 0) {
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_peer<0, 4>, kPcgThreads, 0) != cudaSuccess || nb < 1) {
@@ -542,6 +559,8 @@ ira_status solve_pcg_peer(ira_context* h) {
   pp.pc1 = pairing ? h->pc1.as<double>() : nullptr;
   pp.pc2 = pairing ? h->pc2.as<double>() : nullptr;
   pp.npairs = pairing ? h->npairs.as<int>() : nullptr;
+  pp.mate2 = pairing ? h->mate2.as<int>() : nullptr;
+  pp.pc3 = pairing ? h->pc3.as<double>() : nullptr;
   pp.n = h->peer_n; pp.nslices = h->nslices; pp.max_iters = std::max(0, h->opt.cg_max_iters);
   pp.rtol2 = h->opt.cg_rtol * h->opt.cg_rtol;
   pp.sell_row = h->sell_row.as<int>(); pp.slice_off = h->slice_off.as<int>(); pp.slice_width = h->slice_width.as<int>();
@@ -632,6 +651,10 @@ ira_status alloc_problem(ira_context* h, int64_t m, int n) {
   IRA_CUDA(h, h->pc1.reserve(sizeof(double) * (size_t)std::max(n, 1)));
   IRA_CUDA(h, h->pc2.reserve(sizeof(double) * (size_t)std::max(n, 1)));
   IRA_CUDA(h, h->npairs.reserve(sizeof(int)));
+  IRA_CUDA(h, h->mate2.reserve(sizeof(int) * (size_t)std::max(n, 1)));
+  IRA_CUDA(h, h->pc3.reserve(sizeof(double) * (size_t)std::max(n, 1)));
+  IRA_CUDA(h, h->att_key.reserve(sizeof(unsigned long long) * (size_t)std::max(n, 1)));
+  IRA_CUDA(h, h->sell_pos.reserve(sizeof(int) * (size_t)std::max(n, 1)));
   return IRA_OK;
 }
 
@@ -704,7 +727,9 @@ ira_status build_sell(ira_context* h) {
                                                         h->sell_row.as<int>(), h->slice_off.as<int>(),
                                                         h->slice_width.as<int>(), h->npos, h->sell_col.as<int>(),
                                                         h->sell_eid.as<int>(), h->sell_w2.as<double>());
-  return launch_check(h, "k_sell_fill");
+  IRA_TRY(launch_check(h, "k_sell_fill"));
+  k_sell_inverse<<<cdiv(h->npos, 256), 256, 0, h->stream>>>(h->sell_row.as<int>(), h->npos, h->sell_pos.as<int>());
+  return launch_check(h, "k_sell_inverse");
 }
 
 ira_status upload_Q(ira_context* h, const double* Q, int64_t ld_q, DevBuf& dst) {
@@ -775,6 +800,7 @@ ira_status ira_options_default(ira_options* o) {
   o->cg_max_iters = 20000;
   o->cg_rtol = 1e-10;
   o->pair_theta = 0.2;
+  o->pair_theta3 = 0.05;
   o->cg_check_every = 16;
   o->lanes_per_row = 0;
   o->world_size = 1;
@@ -831,7 +857,7 @@ ira_status ira_destroy(ira_handle h) {
                     &h->R2, &h->S2, &h->pdU, &h->pdAX, &h->pdL1, &h->pdL2, &h->pdADX, &h->pdDU, &h->pdDL1, &h->pdDL2, &h->pdEV,
                     &h->pdSIGX, &h->sell_w3, &h->pdX, &h->pdATV, &h->pdATDV, &h->pdW1P, &h->pdDX, &h->diag3, &h->dinv3,
                     &h->pdctl, &h->pdtrial, &h->mst_label, &h->mst_label2, &h->mst_order, &h->mst_order2, &h->mst_done,
-                    &h->mst_ctl, &h->sell_pos, &h->ipc_stage, &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs})
+                    &h->mst_ctl, &h->sell_pos, &h->ipc_stage, &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs, &h->mate2, &h->pc3, &h->att_key})
     b->release();
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);

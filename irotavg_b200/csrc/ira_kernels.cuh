@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(kRedThreads)
 k_cg_init(const double4* __restrict__ B, const double* __restrict__ diag, double* __restrict__ dinv,
           double4* __restrict__ X, double4* __restrict__ R, double4* __restrict__ Z, double4* __restrict__ P,
           int n, Ctl* ctl, double* partials, const int* __restrict__ mate, const double* __restrict__ pc1,
-          const double* __restrict__ pc2) {
+          const double* __restrict__ pc2, const int* __restrict__ mate2, const double* __restrict__ pc3) {
   __shared__ double sm[6 * 32];
   __shared__ int flag;
   double v[6] = {0, 0, 0, 0, 0, 0};
@@ -348,6 +348,12 @@ k_cg_init(const double4* __restrict__ B, const double* __restrict__ diag, double
         const double4 bm = ldg256(B + mt);
         const double c2 = pc2[i];
         z.x += c2 * bm.x; z.y += c2 * bm.y; z.z += c2 * bm.z;
+        const int m2 = mate2[i];
+        if (m2 >= 0) {
+          const double4 b2 = ldg256(B + m2);
+          const double c3 = pc3[i];
+          z.x += c3 * b2.x; z.y += c3 * b2.y; z.z += c3 * b2.z;
+        }
       }
     }
     st256(X + i, make_double4(0, 0, 0, 0));
@@ -489,7 +495,8 @@ k_cg_update(double4* __restrict__ X, double4* __restrict__ R, double4* __restric
 // complete, hence a kernel of its own after k_cg_update(defer_z = 1).  Then r.z -> beta, convergence.
 __global__ void __launch_bounds__(kRedThreads)
 k_cg_precond(const double4* __restrict__ R, double4* __restrict__ Z, const int* __restrict__ mate,
-             const double* __restrict__ pc1, const double* __restrict__ pc2, int n, Ctl* ctl, double* partials) {
+             const double* __restrict__ pc1, const double* __restrict__ pc2, int n, Ctl* ctl, double* partials,
+             const int* __restrict__ mate2, const double* __restrict__ pc3) {
   if (ctl->done) return;
   __shared__ double sm[3 * 32];
   __shared__ int flag;
@@ -503,6 +510,12 @@ k_cg_precond(const double4* __restrict__ R, double4* __restrict__ Z, const int* 
       const double4 rm = ldg256(R + mt);
       const double c2 = pc2[i];
       z.x += c2 * rm.x; z.y += c2 * rm.y; z.z += c2 * rm.z;
+      const int m2 = mate2[i];
+      if (m2 >= 0) {
+        const double4 r2 = ldg256(R + m2);
+        const double c3 = pc3[i];
+        z.x += c3 * r2.x; z.y += c3 * r2.y; z.z += c3 * r2.z;
+      }
     }
     st256(Z + i, z);
     v[0] += r.x * z.x; v[1] += r.y * z.y; v[2] += r.z * z.z;

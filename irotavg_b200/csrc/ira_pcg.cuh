@@ -303,7 +303,7 @@ __global__ void k_pair_select(const unsigned long long* __restrict__ key_local, 
 __global__ void __launch_bounds__(256)
 k_pair_mate(const unsigned long long* __restrict__ pair_key, const double* __restrict__ pair_w2,
             const double* __restrict__ diag, int n, int* __restrict__ mate, double* __restrict__ pc1,
-            double* __restrict__ pc2, int* __restrict__ npairs) {
+            double* __restrict__ pc2, int* __restrict__ npairs, int* __restrict__ mate2, double* __restrict__ pc3) {
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
     int m = -1;
     const double dv = diag[v];
@@ -326,6 +326,93 @@ k_pair_mate(const unsigned long long* __restrict__ pair_key, const double* __res
     mate[v] = m;
     pc1[v] = c1;
     pc2[v] = c2;
+    mate2[v] = -1;
+    pc3[v] = 0.0;
+  }
+}
+
+// ---- third member: 3x3 blocks -------------------------------------------------------------------------
+// With L1 weights a stiff edge rarely comes alone: a node tied to TWO neighbours by edges 10^3..10^6 times
+// stiffer than the rest is as common as an isolated stiff pair, and a 2x2 block cannot absorb it (numpy study,
+// n = 20k after 29 L1 iterations: Jacobi 8 765, pairs 110, pairs + third member 39 PCG iterations).  After the
+// mutual pairs are fixed, every still-single node proposes to the pair that holds its strongest neighbour
+// (normalised strength >= theta3); a pair takes its strongest applicant (atomicMax on a strength|node key:
+// deterministic) and the 3x3 diagonal block is inverted exactly.
+__global__ void __launch_bounds__(256)
+k_attach_best(const int* __restrict__ sell_row, const int* __restrict__ slice_off, const int* __restrict__ slice_width,
+              const int* __restrict__ sell_col, const double* __restrict__ sell_w2, const double* __restrict__ diag,
+              const int* __restrict__ mate, int nslices, double theta3, unsigned long long* __restrict__ att_key) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (int s = blockIdx.x + gridDim.x * warp; s < nslices; s += gridDim.x * wpb) {
+    const int row = sell_row[s * kSellC + lane];
+    if (row < 0 || mate[row] >= 0) continue;
+    const double dr = diag[row];
+    if (!(dr > 0.0)) continue;
+    const int width = slice_width[s];
+    const int64_t base = (int64_t)slice_off[s] + lane;
+    float best = 0.f;
+    int leader = -1;
+    for (int j = 0; j < width; ++j) {
+      const int64_t o = base + (int64_t)j * kSellC;
+      const double w2 = sell_w2[o];
+      const int c = sell_col[o];
+      if (w2 > 0.0 && c != row) {
+        const int mc = mate[c];
+        if (mc >= 0) {
+          const float st = (float)(w2 / sqrt(dr * diag[c]));
+          const int ld = c < mc ? c : mc;
+          if (st >= (float)theta3 && (st > best || (st == best && ld < leader))) { best = st; leader = ld; }
+        }
+      }
+    }
+    if (leader >= 0)
+      atomicMax(att_key + leader, ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(0xffffffffu - (unsigned)row));
+  }
+}
+
+// One thread per pair leader a (a < b = mate[a]) that got an applicant t: exact inverse of
+//   [[da, -wab, -wat], [-wab, db, -wbt], [-wat, -wbt, dt]]
+// by eliminating a, written with the "excess" e = d - (block couplings) >= 0 so that stiff couplings never
+// cancel: Schur complement of (b, t) = [[w' + xb, -w'], [-w', w' + xt]], w' = wbt + wab wat / da,
+// xb = eb + wab ea / da, xt = et + wat ea / da, det = w' (xb + xt) + xb xt; every entry of the inverse is a
+// sum of non-negative terms.
+__global__ void __launch_bounds__(256)
+k_attach_block(const unsigned long long* __restrict__ att_key, const int* __restrict__ sell_pos,
+               const int* __restrict__ slice_off, const int* __restrict__ slice_width, const int* __restrict__ sell_col,
+               const double* __restrict__ sell_w2, const double* __restrict__ diag, const double* __restrict__ pair_w2,
+               int n, int* __restrict__ mate, int* __restrict__ mate2, double* __restrict__ pc1, double* __restrict__ pc2,
+               double* __restrict__ pc3) {
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+    const unsigned long long key = att_key[a];
+    if (!key) continue;
+    const int b = mate[a];
+    if (b < 0 || b < a) continue;                        // keys are only ever posted to leaders
+    const int t = (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
+    const int pos = sell_pos[t];
+    const int sl = pos / kSellC, ln = pos % kSellC;
+    const int width = slice_width[sl];
+    const int64_t base = (int64_t)slice_off[sl] + ln;
+    double wat = 0.0, wbt = 0.0;
+    for (int j = 0; j < width; ++j) {
+      const int64_t o = base + (int64_t)j * kSellC;
+      const int c = sell_col[o];
+      if (c == a) wat += sell_w2[o];
+      else if (c == b) wbt += sell_w2[o];
+    }
+    const double da = diag[a], db = diag[b], dt = diag[t], wab = pair_w2[a];
+    const double ea = fmax(da - wab - wat, 0.0), eb = fmax(db - wab - wbt, 0.0), et = fmax(dt - wat - wbt, 0.0);
+    const double lb = wab / da, lt = wat / da;
+    const double xb = eb + lb * ea, xt = et + lt * ea;
+    const double wp = wbt + lb * wat;
+    const double det = wp * (xb + xt) + xb * xt;
+    if (!(det > 1e-12 * db * dt)) continue;              // floating 3-node component: keep the pair
+    const double sbb = (wp + xt) / det, sbt = wp / det, stt = (wp + xb) / det;
+    const double iab = lb * sbb + lt * sbt, iat = lb * sbt + lt * stt;
+    const double iaa = 1.0 / da + lb * iab + lt * iat;
+    mate2[a] = t; pc1[a] = iaa; pc2[a] = iab; pc3[a] = iat;
+    mate2[b] = t; pc1[b] = sbb; pc2[b] = iab; pc3[b] = sbt;
+    mate[t] = a; mate2[t] = b; pc1[t] = stt; pc2[t] = iat; pc3[t] = sbt;
   }
 }
 
@@ -338,7 +425,8 @@ struct PcgParams {
   const double4* B; const double* diag;
   double4 *X, *R, *U, *W, *P, *S;
   double* dinv;
-  const int* mate; const double* pc1; const double* pc2; const int* npairs;   // 2x2 block-Jacobi (null: Jacobi)
+  const int* mate; const double* pc1; const double* pc2; const int* npairs;   // 2x2 / 3x3 block-Jacobi (null: Jacobi)
+  const int* mate2; const double* pc3;                                         // third member of a 3x3 block, or -1
   double* partials;      // [gridDim.x][kPcgNV]
   Ctl* ctl;
 };
@@ -408,6 +496,12 @@ k_pcg_persistent(const PcgParams p) {
           const double4 bm = ldg256(p.B + mt);
           const double c2 = p.pc2[row];
           u0.x += c2 * bm.x; u0.y += c2 * bm.y; u0.z += c2 * bm.z;
+          const int m2 = p.mate2[row];
+          if (m2 >= 0) {
+            const double4 b2 = ldg256(p.B + m2);
+            const double c3 = p.pc3[row];
+            u0.x += c3 * b2.x; u0.y += c3 * b2.y; u0.z += c3 * b2.z;
+          }
         }
       }
       st256(p.U + row, u0);
@@ -508,6 +602,12 @@ k_pcg_persistent(const PcgParams p) {
             const double4 rm = ld256(p.R + mt);
             const double c2 = p.pc2[row];
             u.x += c2 * rm.x; u.y += c2 * rm.y; u.z += c2 * rm.z;
+            const int m2 = p.mate2[row];
+            if (m2 >= 0) {
+              const double4 r2 = ld256(p.R + m2);
+              const double c3 = p.pc3[row];
+              u.x += c3 * r2.x; u.y += c3 * r2.y; u.z += c3 * r2.z;
+            }
           }
           st256(p.U + row, u);
         }
@@ -555,7 +655,7 @@ k_pcg_persistent_reg(const PcgRegParams q) {
   const int lane = threadIdx.x & 31;
   const int slice = blockIdx.x + gridDim.x * (threadIdx.x >> 5);     // <= 1 slice per warp
   const bool has_pairs = p.npairs != nullptr && *p.npairs > 0;
-  int row = -1, width = 0, mt = -1;
+  int row = -1, width = 0, mt = -1, mt2 = -1;
   int64_t base = 0;
   if (slice < p.nslices) {
     row = p.sell_row[slice * kSellC + lane];
@@ -566,7 +666,7 @@ k_pcg_persistent_reg(const PcgRegParams q) {
 #pragma unroll
   for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
   double x0 = 0, x1 = 0, x2 = 0, r0 = 0, r1 = 0, r2 = 0, p0 = 0, p1 = 0, p2 = 0, s0 = 0, s1 = 0, s2 = 0;
-  double u0 = 0, u1 = 0, u2 = 0, di = 0, c2 = 0;
+  double u0 = 0, u1 = 0, u2 = 0, di = 0, c2 = 0, c3 = 0;
   if (row >= 0) {
     const double4 b = ldg256(p.B + row);
     const double d = p.diag[row];
@@ -579,6 +679,12 @@ k_pcg_persistent_reg(const PcgRegParams q) {
         c2 = p.pc2[row];
         const double4 bm = ldg256(p.B + mt);
         u0 += c2 * bm.x; u1 += c2 * bm.y; u2 += c2 * bm.z;
+        mt2 = p.mate2[row];
+        if (mt2 >= 0) {
+          c3 = p.pc3[row];
+          const double4 b2 = ldg256(p.B + mt2);
+          u0 += c3 * b2.x; u1 += c3 * b2.y; u2 += c3 * b2.z;
+        }
         st256(q.RS1r + row, b);                                      // "previous" buffer of iteration 0
         st256(q.RS1s + row, make_double4(0, 0, 0, 0));
       }
@@ -652,6 +758,11 @@ k_pcg_persistent_reg(const PcgRegParams q) {
         const double4 rm = ld256(oldR + mt), sm = ld256(oldS + mt), wm = ld256(p.W + mt);
         const double sm0 = wm.x + b0 * sm.x, sm1 = wm.y + b1 * sm.y, sm2 = wm.z + b2 * sm.z;   // the mate's new s
         u0 += c2 * (rm.x - a0 * sm0); u1 += c2 * (rm.y - a1 * sm1); u2 += c2 * (rm.z - a2 * sm2);
+        if (mt2 >= 0) {
+          const double4 rn = ld256(oldR + mt2), sn = ld256(oldS + mt2), wn = ld256(p.W + mt2);
+          const double t0 = wn.x + b0 * sn.x, t1 = wn.y + b1 * sn.y, t2 = wn.z + b2 * sn.z;
+          u0 += c3 * (rn.x - a0 * t0); u1 += c3 * (rn.y - a1 * t1); u2 += c3 * (rn.z - a2 * t2);
+        }
         st256(curR + row, make_double4(r0, r1, r2, 0.0));
         st256(curS + row, make_double4(s0, s1, s2, 0.0));
       }

@@ -60,8 +60,8 @@ struct PcgPeerParams {
   unsigned long long epoch_base;  // flags hold monotonically increasing epochs across launches
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
@@ -91,7 +91,8 @@ __device__ __forceinline__ void peer_barrier(const PcgPeerParams& q, cooperative
   grid.sync();
   if (blockIdx.x == 0 && threadIdx.x < q.world) {
     PeerWindow w = peer_window_at(q.win[threadIdx.x], q.base.n);
-    st_release_sys(w.flags + q.rank, epoch);
+    // relaxed: every block's data stores were fenced system-wide (completed at the peers) before the grid barrier
+    st_relaxed_sys(w.flags + q.rank, epoch);
   }
   if (threadIdx.x < q.world) {
     PeerWindow mine = peer_window_at(q.win[q.rank], q.base.n);
@@ -105,7 +106,7 @@ __device__ __forceinline__ void peer_barrier(const PcgPeerParams& q, cooperative
         else if (now - t0 > 20000000000ull) asm volatile("trap;");
       }
     }
-    __threadfence_system();                                // acquire: the peers' data stores precede their flags
+    __threadfence();     // acquire: drop stale L1 lines; the peers' data is already in this GPU's L2 (its home)
   }
   __syncthreads();
 }
@@ -153,6 +154,12 @@ k_pcg_peer(const PcgPeerParams q) {
           const double4 bm = ldg256(p.B + mt);
           const double c2 = p.pc2[row];
           u0.x += c2 * bm.x; u0.y += c2 * bm.y; u0.z += c2 * bm.z;
+          const int m2 = p.mate2[row];
+          if (m2 >= 0) {
+            const double4 b2 = ldg256(p.B + m2);
+            const double c3 = p.pc3[row];
+            u0.x += c3 * b2.x; u0.y += c3 * b2.y; u0.z += c3 * b2.z;
+          }
           st256(me.MR[1] + row, b);
           st256(me.MS[1] + row, make_double4(0, 0, 0, 0));
         }
@@ -196,7 +203,12 @@ k_pcg_peer(const PcgPeerParams q) {
         st256(p.W + row, w4);
         if (has_pairs) {
           const int mt = p.mate[row];
-          if (mt >= 0) st256(peer_window_at(q.win[peer_owner(q, mt)], p.n).MW + row, w4);   // the mate needs my w
+          if (mt >= 0) {                                                   // my block mates need my w
+            const int o1 = peer_owner(q, mt);
+            st256(peer_window_at(q.win[o1], p.n).MW + row, w4);
+            const int m2 = p.mate2[row];
+            if (m2 >= 0) { const int o2 = peer_owner(q, m2); if (o2 != o1) st256(peer_window_at(q.win[o2], p.n).MW + row, w4); }
+          }
         }
         const double4 r = ld256(p.R + row);
         v[0] += r.x * u.x; v[1] += r.y * u.y; v[2] += r.z * u.z;
@@ -271,9 +283,23 @@ k_pcg_peer(const PcgPeerParams q) {
             const double c2 = p.pc2[row];
             const double sm0 = wm.x + b0 * sm.x, sm1 = wm.y + b1 * sm.y, sm2 = wm.z + b2 * sm.z;
             un.x += c2 * (rm.x - a0 * sm0); un.y += c2 * (rm.y - a1 * sm1); un.z += c2 * (rm.z - a2 * sm2);
-            const PeerWindow mw = peer_window_at(q.win[peer_owner(q, mt)], p.n);
+            const int o1 = peer_owner(q, mt);
+            const PeerWindow mw = peer_window_at(q.win[o1], p.n);
             st256(mw.MR[cur] + row, r);
             st256(mw.MS[cur] + row, ss);
+            const int m2 = p.mate2[row];
+            if (m2 >= 0) {
+              const double4 rn = ld256(me.MR[old] + m2), sn = ld256(me.MS[old] + m2), wn = ld256(me.MW + m2);
+              const double c3 = p.pc3[row];
+              const double t0 = wn.x + b0 * sn.x, t1 = wn.y + b1 * sn.y, t2 = wn.z + b2 * sn.z;
+              un.x += c3 * (rn.x - a0 * t0); un.y += c3 * (rn.y - a1 * t1); un.z += c3 * (rn.z - a2 * t2);
+              const int o2 = peer_owner(q, m2);
+              if (o2 != o1) {
+                const PeerWindow mw2 = peer_window_at(q.win[o2], p.n);
+                st256(mw2.MR[cur] + row, r);
+                st256(mw2.MS[cur] + row, ss);
+              }
+            }
           }
         }
 #pragma unroll
