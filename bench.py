@@ -15,8 +15,14 @@ run; ral/l1_irls.cpp:590) on the synthetic random SO(3) graph n = 100 000 / m = 
              a profiled step, against MEASURED_PEAKS.json's HBM copy bandwidth.
   cpu_baseline  the oracle port (numpy/scipy restatement or, when built, the C restatement) timed
              on the host cores on a bounded sample of the same call.
-N > 1 (launched by torchrun, one rank per GPU): the SAME graph with its edges sharded over the
-ranks (strong scaling), node vectors all-reduced with NCCL once per PCG iteration.
+N > 1 (launched by torchrun, one rank per GPU): WEAK scaling - the graph grows with the job, n = 100 000 N
+nodes / m = 1 000 000 N edges (same recipe and seed; N = 8 is configs[3]'s 1M-node / 10M-edge scale), the rows
+of the normal equations are partitioned over the ranks and one persistent kernel per rank runs each solve,
+exchanging through NVLink peer memory.  `value` = IRLS iterations/s x N, i.e. in units of the 1M-edge graph
+(edge-iterations per second / 1e6), so that perfect weak scaling reads N x the single-GPU value.  The line also
+carries `strong_scaling_1M_edges`: plain IRLS iterations/s of the SAME 1M-edge graph on N GPUs - at that size
+one PCG iteration (15 us of SpMV) is shorter than the two NVLink barrier latencies it needs, so it does not
+scale; DESIGN.md has the breakdown.
 `--impl reference` times the CPU port alone (the reference itself cannot be built here: no Eigen /
 SuiteSparse in the image).
 """
@@ -103,9 +109,9 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_graph():
+def make_graph(scale=1):
     from oracle import graphs as G
-    return G.random_graph(n=N_NODES, m=M_EDGES)
+    return G.random_graph(n=N_NODES * scale, m=M_EDGES * scale)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -140,9 +146,10 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    g = make_graph()
+    scale = max(1, args.gpus)                      # the same workload as our arm at N GPUs (weak scaling: graph x N)
+    g = make_graph(scale)
     cost = COSTS[args.cost]
-    sample_iters = args.ref_iters
+    sample_iters = max(3, args.ref_iters // scale)
     for _ in range(min(args.warmup, 1)):
         cpu_port_run(g, cost, 1)
     vals = []
@@ -153,12 +160,12 @@ def run_reference_arm(args):
         v, kind, cores, sample, extra = cpu_port_run(g, cost, sample_iters)
         vals.append(v)
     dt = time.perf_counter() - t_all
-    value = sample_iters * args.steps / dt
+    value = scale * sample_iters * args.steps / dt          # units of the 1M-edge graph, like our arm
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, scale),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, **extra},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -167,8 +174,9 @@ def run_reference_arm(args):
 
 
 def workload_config(args, world):
+    tag = "configs[2]" if world == 1 else f"configs[2] recipe scaled x{world} (weak scaling; x8 = configs[3] scale)"
     return {
-        "workload": f"configs[2]: synthetic random SO(3) graph n={N_NODES} m={M_EDGES} (path + uniform pairs, "
+        "workload": f"{tag}: synthetic random SO(3) graph n={N_NODES * world} m={M_EDGES * world} (path + uniform pairs, "
                     f"sigma_n=0.05 rad, 10% outliers, seed 20190319), {IRLS_ITERS} IRLS iters per step, cost {args.cost}, "
                     "sigma 5 deg, f=1",
         "cost": args.cost, "irls_iters_per_step": IRLS_ITERS, "cg_rtol": 1e-10,
@@ -199,7 +207,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    g = make_graph()
+    g = make_graph(world)
     cost = COSTS[args.cost]
     m, n, f = g.m, g.n, g.f
     from irotavg_b200.sharding import broadcast_unique_id, edge_shard
@@ -280,7 +288,7 @@ def run_ours(args):
     wall_ms = (time.perf_counter() - t_wall0) * 1000.0
     clocks = sampler.stop() if rank == 0 else None
     dev_ms = max_over_ranks(dev_ms)
-    value = IRLS_ITERS * args.steps / (dev_ms / 1000.0)
+    value = world * IRLS_ITERS * args.steps / (dev_ms / 1000.0)        # units of the 1M-edge graph (m = world x 1M)
     Q_res, w_res = s.download()
 
     # ---- the callers' default cost and Huber on the same graph (1 warm-up + 2 timed steps each) ----
@@ -301,8 +309,37 @@ def run_ours(args):
             b.synchronize()
             ms += a.elapsed_time(b)
         ms = max_over_ranks(ms)
-        other[nm] = {"value": IRLS_ITERS * 2 / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms / 2,
+        other[nm] = {"value": world * IRLS_ITERS * 2 / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms / 2,
                      "cg_iters_per_step": int(sum(oi.cg_iters))}
+
+    # ---- N > 1: the same 1M-edge graph on N GPUs (strong scaling), 1 warm-up + 2 timed steps ------------
+    strong = None
+    if world > 1:
+        g1 = make_graph(1)
+        if shard_mode == 1:
+            s.upload(g1.QQ, g1.I, g1.Q0, g1.f)
+        else:
+            lo1, hi1 = edge_shard(g1.m, world, rank)
+            s.upload(np.asfortranarray(g1.QQ[lo1:hi1]), np.ascontiguousarray(g1.I[lo1:hi1]), g1.Q0, g1.f)
+        s.irls_resident(cost, SIGMA, IRLS_ITERS, -1.0)
+        barrier()
+        ms = 0.0
+        for _ in range(2):
+            with torch.cuda.stream(ext):
+                flush.zero_()
+                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+                a.record(ext)
+                si = s.irls_resident(cost, SIGMA, IRLS_ITERS, -1.0)
+                b.record(ext)
+            b.synchronize()
+            ms += a.elapsed_time(b)
+        ms = max_over_ranks(ms)
+        ph = si.profile.get("pcg_phases") or {}
+        strong = {"value": IRLS_ITERS * 2 / (ms / 1000.0), "unit": "irls_iters/s (n=100000, m=1000000)", "ms_per_step": ms / 2,
+                  "cg_iters_per_step": int(sum(si.cg_iters)),
+                  "pcg_us_per_iteration": 1e3 * ph.get("kernel_ms", 0.0) / max(1, int(sum(si.cg_iters)))}
+        s.upload(QQ_loc, I_loc, g.Q0, f)
+        del g1
 
     # ---- e2e arm: host-buffer C-ABI call, pinned buffers --------------------------------------
     def pinned(a, order):
@@ -336,7 +373,7 @@ def run_ours(args):
         e2e_ms += ms
     barrier()
     e2e_ms = max_over_ranks(e2e_ms)
-    e2e_value = IRLS_ITERS * e2e_steps / (e2e_ms / 1000.0)
+    e2e_value = world * IRLS_ITERS * e2e_steps / (e2e_ms / 1000.0)
     h2d = I_loc.nbytes + QQ_loc.nbytes + Q0f.nbytes
     d2h = Q0f.nbytes + 8 * m_loc
     same = bool(np.array_equal(np.ascontiguousarray(pQ), Q_res))
@@ -405,7 +442,7 @@ def run_ours(args):
         info = infos[-1]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
@@ -422,6 +459,11 @@ def run_ours(args):
             line["kernel_time_share_multikernel_path"] = prof_share
         if other:
             line["other_costs"] = other
+        if strong is not None:
+            line["strong_scaling_1M_edges"] = strong
+        if world > 1:
+            ph = info.profile.get("pcg_phases") or {}
+            line["pcg_us_per_iteration"] = 1e3 * ph.get("kernel_ms", 0.0) / max(1, int(sum(info.cg_iters)))
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

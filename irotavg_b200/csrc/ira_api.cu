@@ -537,7 +537,7 @@ ira_status peer_setup(ira_context* h) {
   h->peer_n = n;
   if (h->peer_blocks_per_sm == 0) {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_peer<0, 4>, kPcgThreads, 0) != cudaSuccess || nb < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_peer<0, 4>, kPeerThreads, 0) != cudaSuccess || nb < 1) {
       cudaGetLastError();
       h->err = "k_pcg_peer cannot be launched cooperatively on this device";
       return IRA_ERR_CUDA;
@@ -581,7 +581,7 @@ ira_status solve_pcg_peer(ira_context* h) {
   ProfScope ps(h, KC_PCG);
   void* args[] = {(void*)&q};
   void* fn = h->opt.spmv_variant == 1 ? (void*)k_pcg_peer<1, 4> : (void*)k_pcg_peer<0, 4>;
-  IRA_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPcgThreads), args, 0, h->stream));
+  IRA_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPeerThreads), args, 0, h->stream));
   h->launches++;
   const PeerWindow me = peer_window_at((unsigned char*)h->peer_win.p, h->peer_n);
   IRA_CUDA(h, cudaMemcpyAsync(h->X.p, me.X, sizeof(double4) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));

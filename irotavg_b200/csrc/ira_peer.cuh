@@ -26,6 +26,7 @@
 namespace ira {
 
 constexpr int kPeerMax = 8;
+constexpr int kPeerThreads = 512;      // 16 warps: 128 registers per thread (768 threads spilled 320 B)
 
 // Layout of the per-rank window (one cudaMalloc, exported with cudaIpcGetMemHandle).
 struct PeerWindow {
@@ -120,7 +121,7 @@ __device__ __forceinline__ int peer_owner(const PcgPeerParams& q, int row) {
 }
 
 template <int V, int UNR>
-__global__ void __launch_bounds__(kPcgThreads, 1)
+__global__ void __launch_bounds__(kPeerThreads, 1)
 k_pcg_peer(const PcgPeerParams q) {
   namespace cgx = cooperative_groups;
   const PcgParams& p = q.base;
