@@ -438,6 +438,17 @@ def run_ours(args):
         s2.close()
         rms = O.geodesic_rms(Q2, ref.Q, f)
 
+    # ---- configs[4] (incremental rotAvg stream), bounded sample: first 1500 frames of the 10k-frame stream -------
+    stream = None
+    if rank == 0 and world == 1 and not args.no_stream:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_stream
+            stream = bench_stream.run(frames=1500, loop_every=500, cpu_frames=40)
+            stream["sample"] = "first 1500 frames of the 10 000-frame stream (tools/bench_stream.py runs all of it)"
+        except Exception as e:                           # the headline line must not depend on g++ being present
+            stream = {"error": repr(e)}
+
     if rank == 0:
         info = infos[-1]
         line = {
@@ -464,6 +475,8 @@ def run_ours(args):
         if world > 1:
             ph = info.profile.get("pcg_phases") or {}
             line["pcg_us_per_iteration"] = 1e3 * ph.get("kernel_ms", 0.0) / max(1, int(sum(info.cg_iters)))
+        if stream is not None:
+            line["config5_rotavg_stream"] = stream
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -481,6 +494,7 @@ def main():
     ap.add_argument("--cost", default="L1", choices=sorted(COSTS))
     ap.add_argument("--nccl-allreduce", action="store_true",
                     help="N > 1: edge shards + NCCL all-reduce per PCG iteration instead of the peer-memory solve")
+    ap.add_argument("--no-stream", action="store_true", help="skip the bounded configs[4] rotAvg-stream sample")
     ap.add_argument("--ref-iters", type=int, default=10, help="IRLS iterations in the CPU port's bounded sample")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -22,12 +22,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=10000)
-    ap.add_argument("--loop-every", type=int, default=500)
-    ap.add_argument("--cpu-frames", type=int, default=150)
-    args = ap.parse_args()
+def run(frames=10000, loop_every=500, cpu_frames=150):
+    class A:
+        pass
+    args = A()
+    args.frames, args.loop_every, args.cpu_frames = frames, loop_every, cpu_frames
     from irotavg_b200 import build
     from oracle import irls_oracle as O
     from oracle import rotavg_stream as RS
@@ -81,7 +80,16 @@ def main():
         ns = sum(1 for r in reps if r["solved"])
         line["cpu_baseline"] = {"value": ns / dt, "unit": "calls/s", "cores": 1, "kind": "port",
                                 "sample": f"first {args.cpu_frames} calls of the same stream, oracle/rotavg_stream.py"}
-    print(json.dumps(line))
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=10000)
+    ap.add_argument("--loop-every", type=int, default=500)
+    ap.add_argument("--cpu-frames", type=int, default=150)
+    args = ap.parse_args()
+    print(json.dumps(run(args.frames, args.loop_every, args.cpu_frames)))
 
 
 if __name__ == "__main__":
