@@ -429,14 +429,15 @@ ira_status run_pairing(ira_context* h) {
     k_attach_best<<<grid_slices(h), 256, 0, h->stream>>>(h->sell_row.as<int>(), h->slice_off.as<int>(),
                                                        h->slice_width.as<int>(), h->sell_col.as<int>(),
                                                        h->sell_w2.as<double>(), h->diag.as<double>(), h->mate.as<int>(),
-                                                       h->nslices, h->opt.pair_theta3, h->att_key.as<unsigned long long>());
+                                                       h->nslices, h->opt.pair_theta3, h->att_key.as<unsigned long long>(),
+                                                       h->npairs.as<int>());
     IRA_TRY(launch_check(h, "k_attach_best"));
     k_attach_block<<<grid_nodes(h, h->n), 256, 0, h->stream>>>(h->att_key.as<unsigned long long>(), h->sell_pos.as<int>(),
                                                               h->slice_off.as<int>(), h->slice_width.as<int>(),
                                                               h->sell_col.as<int>(), h->sell_w2.as<double>(),
                                                               h->diag.as<double>(), h->pair_w2.as<double>(), h->n,
                                                               h->mate.as<int>(), h->mate2.as<int>(), h->pc1.as<double>(),
-                                                              h->pc2.as<double>(), h->pc3.as<double>());
+                                                              h->pc2.as<double>(), h->pc3.as<double>(), h->npairs.as<int>());
     IRA_TRY(launch_check(h, "k_attach_block"));
   }
   return IRA_OK;

@@ -96,21 +96,28 @@ k_sell_rhs(const int* __restrict__ sell_row, const int* __restrict__ slice_off, 
     const int width = slice_width[s];
     const int64_t base = (int64_t)slice_off[s] + lane;
     double bx = 0, by = 0, bz = 0, d = 0;
-#pragma unroll 4
-    for (int j = 0; j < width; ++j) {
-      const int64_t o = base + (int64_t)j * kSellC;
-      const int eid = sell_eid[o];
-      double w2 = 0.0;
-      if (eid != kSellPad) {
-        const bool neg = eid < 0;
-        const int kk = neg ? ~eid : eid;
-        const double4 w = ldg256(wres + (kk & kEidMask));
-        w2 = (kk & kEidQuirk) ? 0.0 : w.w;                   // make_A drops (free i, fixed j) edges
-        d += w2;
-        const double sg = neg ? -w2 : w2;
-        bx += sg * w.x; by += sg * w.y; bz += sg * w.z;
+    for (int j = 0; j < width; j += 4) {                     // widths are multiples of 4: 4 independent gathers in flight
+      int eid[4]; double4 w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) eid[q] = __ldg(sell_eid + base + (int64_t)(j + q) * kSellC);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int kk = eid[q] < 0 ? ~eid[q] : eid[q];
+        w[q] = eid[q] != kSellPad ? ldg256(wres + (kk & kEidMask)) : make_double4(0, 0, 0, 0);
       }
-      sell_w2[o] = w2;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        double w2 = 0.0;
+        if (eid[q] != kSellPad) {
+          const bool neg = eid[q] < 0;
+          const int kk = neg ? ~eid[q] : eid[q];
+          w2 = (kk & kEidQuirk) ? 0.0 : w[q].w;                // make_A drops (free i, fixed j) edges
+          d += w2;
+          const double sg = neg ? -w2 : w2;
+          bx += sg * w[q].x; by += sg * w[q].y; bz += sg * w[q].z;
+        }
+        sell_w2[base + (int64_t)(j + q) * kSellC] = w2;
+      }
     }
     if (row >= 0) {
       st256(B + row, make_double4(bx, by, bz, 0.0));
@@ -267,17 +274,23 @@ k_pair_best(const int* __restrict__ sell_row, const int* __restrict__ slice_off,
     unsigned long long best = 0ull;
     double bw = 0.0;
     if (dr > 0.0) {
-      for (int j = 0; j < width; ++j) {
-        const int64_t o = base + (int64_t)j * kSellC;
-        const double w2 = sell_w2[o];
-        const int c = sell_col[o];
-        if (w2 > 0.0 && c != row) {
-          const double dc = diag[c];
-          if (dc > 0.0) {                                   // fixed nodes (diag 0) never pair
-            const float st = (float)(w2 / sqrt(dr * dc));
+      for (int j = 0; j < width; j += 4) {                   // 4 independent diag gathers in flight
+        double w2[4], dc[4]; int c[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int64_t o = base + (int64_t)(j + q) * kSellC;
+          w2[q] = sell_w2[o];
+          c[q] = sell_col[o];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dc[q] = diag[c[q]];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (w2[q] > 0.0 && c[q] != row && dc[q] > 0.0) {      // fixed nodes (diag 0) never pair
+            const float st = (float)(w2[q] / sqrt(dr * dc[q]));
             if (st >= (float)theta) {
-              const unsigned long long key = ((unsigned long long)__float_as_uint(st) << 32) | (unsigned long long)(0xffffffffu - (unsigned)c);
-              if (key > best) { best = key; bw = w2; }
+              const unsigned long long key = ((unsigned long long)__float_as_uint(st) << 32) | (unsigned long long)(0xffffffffu - (unsigned)c[q]);
+              if (key > best) { best = key; bw = w2[q]; }
             }
           }
         }
@@ -341,7 +354,9 @@ k_pair_mate(const unsigned long long* __restrict__ pair_key, const double* __res
 __global__ void __launch_bounds__(256)
 k_attach_best(const int* __restrict__ sell_row, const int* __restrict__ slice_off, const int* __restrict__ slice_width,
               const int* __restrict__ sell_col, const double* __restrict__ sell_w2, const double* __restrict__ diag,
-              const int* __restrict__ mate, int nslices, double theta3, unsigned long long* __restrict__ att_key) {
+              const int* __restrict__ mate, int nslices, double theta3, unsigned long long* __restrict__ att_key,
+              const int* __restrict__ npairs) {
+  if (*npairs == 0) return;                               // no 2x2 block to join (mild weights: L2, Geman-McClure ...)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   for (int s = blockIdx.x + gridDim.x * warp; s < nslices; s += gridDim.x * wpb) {
@@ -353,15 +368,21 @@ k_attach_best(const int* __restrict__ sell_row, const int* __restrict__ slice_of
     const int64_t base = (int64_t)slice_off[s] + lane;
     float best = 0.f;
     int leader = -1;
-    for (int j = 0; j < width; ++j) {
-      const int64_t o = base + (int64_t)j * kSellC;
-      const double w2 = sell_w2[o];
-      const int c = sell_col[o];
-      if (w2 > 0.0 && c != row) {
-        const int mc = mate[c];
-        if (mc >= 0) {
-          const float st = (float)(w2 / sqrt(dr * diag[c]));
-          const int ld = c < mc ? c : mc;
+    for (int j = 0; j < width; j += 4) {
+      double w2[4], dc[4]; int c[4], mc[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t o = base + (int64_t)(j + q) * kSellC;
+        w2[q] = sell_w2[o];
+        c[q] = sell_col[o];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { mc[q] = mate[c[q]]; dc[q] = diag[c[q]]; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (w2[q] > 0.0 && c[q] != row && mc[q] >= 0) {
+          const float st = (float)(w2[q] / sqrt(dr * dc[q]));
+          const int ld = c[q] < mc[q] ? c[q] : mc[q];
           if (st >= (float)theta3 && (st > best || (st == best && ld < leader))) { best = st; leader = ld; }
         }
       }
@@ -382,7 +403,8 @@ k_attach_block(const unsigned long long* __restrict__ att_key, const int* __rest
                const int* __restrict__ slice_off, const int* __restrict__ slice_width, const int* __restrict__ sell_col,
                const double* __restrict__ sell_w2, const double* __restrict__ diag, const double* __restrict__ pair_w2,
                int n, int* __restrict__ mate, int* __restrict__ mate2, double* __restrict__ pc1, double* __restrict__ pc2,
-               double* __restrict__ pc3) {
+               double* __restrict__ pc3, const int* __restrict__ npairs) {
+  if (*npairs == 0) return;
   for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
     const unsigned long long key = att_key[a];
     if (!key) continue;
