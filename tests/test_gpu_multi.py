@@ -57,37 +57,37 @@ PEER_WORKER = textwrap.dedent("""
     sigma = 5 * np.pi / 180
     s = ira.Solver(device=lr, world_size=world, rank=rank, shard_mode=1)
     s.comm_init(broadcast_unique_id(dist, ira.Solver, rank, device="cuda"))
+    ref = np.load(os.environ["IRA_REF"])                # oracle results computed once by the parent process
     ok = True
-    graphs = [G.small_graph(n=3000, extra=30000, sigma_n=0.03, outlier_frac=0.1, seed=41, f=2, fixed_anywhere=True),
-              G.small_graph(n=40000, extra=300000, sigma_n=0.05, outlier_frac=0.1, seed=42)]
-    for gi, g in enumerate(graphs):
-        for cost, its in ((O.L1, 14), (O.GEMAN_MCCLURE, 6)):      # 14 L1 iterations: stiff 2x2 blocks across ranks
+    for gi, kw in enumerate(eval(os.environ["IRA_GRAPHS"])):
+        g = G.small_graph(**kw)
+        for cost, its in ((O.L1, 14), (O.GEMAN_MCCLURE, 6)):      # 14 L1 iterations: stiff 2x2 / 3x3 blocks across ranks
             Q, w, info = s.irls(g.QQ, g.I, None, cost, sigma, g.Q0, g.f, its, -1.0)
-            if gi == 0:
-                ref = O.irls(g.QQ, g.I, None, cost, sigma, g.Q0, g.f, its, -1.0, solver="direct")
-            else:
-                ref = O.irls(g.QQ, g.I, None, cost, sigma, g.Q0, g.f, its, -1.0, solver="pcg", pcg_rtol=1e-12)
-            rms = O.geodesic_rms(Q, ref.Q, g.f)
-            wok = np.allclose(w, ref.weights, rtol=1e-5, atol=1e-8)
+            rms = O.geodesic_rms(Q, ref[f"Q_{gi}_{cost}"], g.f)
+            wok = np.allclose(w, ref[f"w_{gi}_{cost}"], rtol=1e-5, atol=1e-8)
             t = torch.from_numpy(np.ascontiguousarray(Q)).cuda()
             t0 = t.clone(); dist.broadcast(t0, 0)
             same = bool(torch.equal(t, t0))                  # replicas are bitwise identical across ranks
-            print(f"rank {rank} graph {gi} cost {cost} cg {info.cg_iters} rms {rms:.2e} weights {wok} identical {same} "
-                  f"ms {info.profile}", flush=True)
+            ph = info.profile.get("pcg_phases", {})
+            print(f"rank {rank}/{world} graph {gi} cost {cost} cg {sum(info.cg_iters)} rms {rms:.2e} weights {wok} "
+                  f"identical {same} pcg kernel {ph.get('kernel_ms', 0):.2f} ms", flush=True)
             ok = ok and rms <= 1e-8 and wok and same and info.cg_hit_max == 0
     s.close()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 """)
 
+PEER_GRAPHS = [dict(n=3000, extra=30000, sigma_n=0.03, outlier_frac=0.1, seed=41, f=2, fixed_anywhere=True),
+               dict(n=20000, extra=150000, sigma_n=0.05, outlier_frac=0.1, seed=42)]
 
-def _torchrun(tmp_path, text, nproc, timeout=900):
+
+def _torchrun(tmp_path, text, nproc, timeout=900, extra_env=None):
     script = tmp_path / "worker.py"
     script.write_text(text)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    env = dict(os.environ, IRA_ROOT=ROOT)
+    env = dict(os.environ, IRA_ROOT=ROOT, **(extra_env or {}))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr",
            "127.0.0.1", "--master-port", str(port), str(script)]
     return subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
@@ -97,10 +97,22 @@ def test_peer_memory_solve(tmp_path, built_lib):
     """shard_mode 1: rows partitioned over the ranks, one persistent kernel per rank, exchange through NVLink peer
     memory (ira_peer.cuh).  Every rank holds the whole graph; results must match the oracle and each other bitwise."""
     import irotavg_b200 as ira
+    import numpy as np
+    from oracle import graphs as G, irls_oracle as O
     nd = ira.device_count()
     if nd < 2:
         pytest.skip("needs 2 GPUs")
-    res = _torchrun(tmp_path, PEER_WORKER, min(nd, 8) if nd in (2, 4, 8) else 2)
+    sigma = 5 * np.pi / 180
+    ref = {}
+    for gi, kw in enumerate(PEER_GRAPHS):
+        g = G.small_graph(**kw)
+        for cost, its in ((O.L1, 14), (O.GEMAN_MCCLURE, 6)):
+            r = (O.irls(g.QQ, g.I, None, cost, sigma, g.Q0, g.f, its, -1.0, solver="direct") if gi == 0 else
+                 O.irls(g.QQ, g.I, None, cost, sigma, g.Q0, g.f, its, -1.0, solver="pcg", pcg_rtol=1e-12))
+            ref[f"Q_{gi}_{cost}"], ref[f"w_{gi}_{cost}"] = r.Q, r.weights
+    np.savez(tmp_path / "ref.npz", **ref)
+    res = _torchrun(tmp_path, PEER_WORKER, min(nd, 8) if nd in (2, 4, 8) else 2,
+                    extra_env={"IRA_REF": str(tmp_path / "ref.npz"), "IRA_GRAPHS": repr(PEER_GRAPHS)})
     print(res.stdout[-3000:])
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
 
