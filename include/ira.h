@@ -79,7 +79,8 @@ typedef struct ira_options {
                               the rows of A^T D^2 A are partitioned over the ranks and ONE persistent kernel per
                               rank runs the solve, exchanging vector slices / dot products / barrier flags by
                               loads and stores into the peers' HBM over NVLink (CUDA IPC mappings,
-                              irotavg_b200/csrc/ira_peer.cuh); weights come back whole on every rank          */
+                              irotavg_b200/csrc/ira_peer.cuh); weights come back whole on every rank.  1 = barrier-free
+                              exchange (self-validating data), 2 = the same with two cross-GPU barriers per iteration */
   int32_t reserved[3];
   double  pair_theta3;     /* a still-single node joins the pair holding its strongest neighbour when that edge's
                               normalised strength is >= pair_theta3 (3x3 blocks, inverted exactly); 0 = pairs only.

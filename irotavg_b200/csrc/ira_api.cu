@@ -500,7 +500,7 @@ ira_status peer_setup(ira_context* h) {
   if (G > kPeerMax) { h->err = "peer-memory solve supports at most 8 ranks"; return IRA_ERR_INVALID_ARG; }
   if (!h->comm) { h->err = "world_size > 1 but ira_comm_init was not called"; return IRA_ERR_COMM; }
   void* before = h->peer_win.p;
-  IRA_CUDA(h, h->peer_win.reserve(peer_window_bytes(n)));
+  IRA_CUDA(h, h->peer_win.reserve(std::max(peer_window_bytes(n), peer_window_ll_bytes(n))));
   // every rank takes the same decision: all see the same n, and a window only ever grows
   if (h->peer_win.p != before || h->peer_exported != h->peer_win.p) {
     for (int g = 0; g < kPeerMax; ++g)
@@ -581,10 +581,11 @@ ira_status solve_pcg_peer(ira_context* h) {
   const int grid = std::max(1, std::min(own, h->sms * h->peer_blocks_per_sm));
   ProfScope ps(h, KC_PCG);
   void* args[] = {(void*)&q};
-  void* fn = h->opt.spmv_variant == 1 ? (void*)k_pcg_peer<1, 4> : (void*)k_pcg_peer<0, 4>;
+  const bool ll = h->opt.shard_mode == 1;                // 2 = the barrier version (A/B measurements)
+  void* fn = ll ? (void*)k_pcg_peer_ll : (h->opt.spmv_variant == 1 ? (void*)k_pcg_peer<1, 4> : (void*)k_pcg_peer<0, 4>);
   IRA_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPeerThreads), args, 0, h->stream));
   h->launches++;
-  const PeerWindow me = peer_window_at((unsigned char*)h->peer_win.p, h->peer_n);
+  const PeerWindow me = peer_window_at((unsigned char*)h->peer_win.p, h->peer_n);   // X sits at the same offset in both layouts
   IRA_CUDA(h, cudaMemcpyAsync(h->X.p, me.X, sizeof(double4) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
   return IRA_OK;
 }
@@ -896,7 +897,7 @@ ira_status ira_problem_upload(ira_handle h, int64_t m, int64_t n_total, int32_t 
   }
   h->persistent = !h->fmt_csr && h->opt.world_size <= 1 && (h->opt.solver & 3) != 1 && h->pcg_blocks_per_sm > 0;
   h->peer = false;
-  if (h->opt.world_size > 1 && h->opt.shard_mode == 1) {
+  if (h->opt.world_size > 1 && (h->opt.shard_mode == 1 || h->opt.shard_mode == 2)) {
     if (h->fmt_csr || h->pcg_blocks_per_sm <= 0) { h->err = "peer-memory solve needs the SELL pattern and cooperative launch"; return IRA_ERR_INVALID_ARG; }
     IRA_TRY(peer_setup(h));
     h->peer = true;

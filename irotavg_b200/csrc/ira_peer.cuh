@@ -22,6 +22,7 @@
 #include <stdint.h>
 
 #include "ira_pcg.cuh"
+#include "ira_mst.cuh"      // ldcg256
 
 namespace ira {
 
@@ -38,16 +39,17 @@ struct PeerWindow {
   double* dots;      // [2][kPeerMax][16]
   unsigned long long* flags;   // [kPeerMax]
 };
-__host__ __device__ inline size_t peer_window_bytes(int n) {
-  return (size_t)7 * n * sizeof(double4) + 2 * kPeerMax * 16 * sizeof(double) + kPeerMax * sizeof(unsigned long long) + 256;
-}
+// The header (flags, dot-product slots) sits at FIXED offsets in front of the vectors, so that a later upload
+// with another n moves only arrays that every solve re-initialises before reading.
+constexpr size_t kPeerHdr = 8192;       // flags at 0 (64 B), dot slots at 256 (2 x 8 x 32 doubles = 4 KB)
+__host__ __device__ inline size_t peer_window_bytes(int n) { return kPeerHdr + (size_t)7 * n * sizeof(double4); }
 __host__ __device__ inline PeerWindow peer_window_at(unsigned char* base, int n) {
   PeerWindow w;
-  double4* v = reinterpret_cast<double4*>(base);
+  double4* v = reinterpret_cast<double4*>(base + kPeerHdr);
   w.U = v; w.X = v + (size_t)n; w.MR[0] = v + (size_t)2 * n; w.MR[1] = v + (size_t)3 * n;
   w.MS[0] = v + (size_t)4 * n; w.MS[1] = v + (size_t)5 * n; w.MW = v + (size_t)6 * n;
-  w.dots = reinterpret_cast<double*>(v + (size_t)7 * n);
-  w.flags = reinterpret_cast<unsigned long long*>(w.dots + 2 * kPeerMax * 16);
+  w.flags = reinterpret_cast<unsigned long long*>(base);
+  w.dots = reinterpret_cast<double*>(base + 256);
   return w;
 }
 
@@ -305,7 +307,7 @@ k_pcg_peer(const PcgPeerParams q) {
         }
 #pragma unroll
         for (int g = 0; g < kPeerMax; ++g)
-          if (g < q.world) st256(reinterpret_cast<double4*>(q.win[g]) + row, un);       // window offset 0 = U
+          if (g < q.world) st256(reinterpret_cast<double4*>(q.win[g] + kPeerHdr) + row, un);   // U is the first vector
       }
     }
     ++it;
@@ -322,6 +324,375 @@ k_pcg_peer(const PcgPeerParams q) {
     }
   }
   peer_barrier(q, grid, ++epoch);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    p.ctl->epoch = epoch;
+    p.ctl->cg_iters = it;
+    for (int c = 0; c < 3; ++c) { p.ctl->bnorm2[c] = sc_bb[c]; p.ctl->rnorm2[c] = sc_rr[c]; }
+    p.ctl->done = 1;
+    unsigned long long ns_end;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_end));
+    p.ctl->cyc_spmv += c_spmv;
+    p.ctl->cyc_update += c_upd;
+    p.ctl->cyc_total += clock64() - c_begin;
+    p.ctl->ns_total += (long long)(ns_end - ns_begin);
+    p.ctl->pcg_spmv_phases += c_spmv > 0 ? it + 1 : 0;
+  }
+}
+
+// =====================================================================================================
+// Barrier-free ("LL") variant.  The barrier version above pays ~31 us of fixed cost per PCG iteration on 2
+// GPUs (tools/peer_probe.py): each cross-GPU barrier needs a system fence that waits for the acknowledgement
+// of every outstanding NVLink store, a grid barrier, a flag flight and a poll.  Here no barrier and no fence
+// separate the iterations - every exchanged datum validates itself:
+//   * u rows: the owner forces the least-significant mantissa bit of each of the 3 doubles to the PARITY of
+//     the iteration that will consume them (a <= 1 ulp change, applied before anybody - the owner included -
+//     uses the value, so all ranks still compute with identical numbers).  An 8-byte store is single-copy
+//     atomic, so each component is individually valid or stale; a gather whose 3 parity bits do not match
+//     simply re-reads (L2-coherent load) until the row has arrived - from another SM or another GPU alike,
+//     which also removes the LOCAL grid barrier after the vector update;
+//   * dot products: {value, epoch} in one 16-byte store (single-copy atomic), polled per value;
+//   * (r, s, w) copies for 2x2 / 3x3 blocks: parity-tagged like u, in buffers indexed by that parity.
+// What is left per iteration: ONE local grid barrier (inside the block-ordered dot-product reduction) and one
+// NVLink store->poll flight.  Write-after-read safety comes from the dot products themselves: a rank sends its
+// partial sums only after all its blocks finished the SpMV (reading u), and nobody can produce the next u
+// before it has received every rank's partial sums.
+// =====================================================================================================
+__device__ __forceinline__ double tag_lsb(double v, int p) {
+  return __longlong_as_double((__double_as_longlong(v) & ~1ll) | (long long)p);
+}
+__device__ __forceinline__ bool has_tag(const double4& v, int p) {
+  return (((__double_as_longlong(v.x) ^ p) | (__double_as_longlong(v.y) ^ p) | (__double_as_longlong(v.z) ^ p)) & 1ll) == 0;
+}
+__device__ __forceinline__ double4 tag4(double x, double y, double z, int p) {
+  return make_double4(tag_lsb(x, p), tag_lsb(y, p), tag_lsb(z, p), 0.0);
+}
+// L2-coherent load of a tagged row; spins until all three components carry parity p.
+__device__ __forceinline__ double4 ld_tagged(const double4* ptr, int p) {
+  double4 v = ldcg256(ptr);
+  if (!has_tag(v, p)) {
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
+    do {
+      __nanosleep(20);
+      v = ldcg256(ptr);
+      if ((++spins & 0x3fffu) == 0u) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 20000000000ull) asm volatile("trap;");
+      }
+    } while (!has_tag(v, p));
+  }
+  return v;
+}
+__device__ __forceinline__ void st_dot16(double* slot, double v, unsigned long long epoch) {
+  asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" :: "l"(slot), "l"(__double_as_longlong(v)), "l"(epoch) : "memory");
+}
+__device__ __forceinline__ double ld_dot16(const double* slot, unsigned long long epoch) {
+  long long v; unsigned long long e;
+  unsigned long long t0 = 0;
+  unsigned int spins = 0;
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(v), "=l"(e) : "l"(slot) : "memory");
+    if (e == epoch) break;
+    if ((++spins & 0xfffu) == 0u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) asm volatile("trap;");
+    }
+  }
+  return __longlong_as_double(v);
+}
+
+// one lane's row of (A^T D^2 A) u with self-validating gathers (4 in flight)
+__device__ __forceinline__ void sell_row_apply_tagged(const int* __restrict__ sell_col, const double* __restrict__ sell_w2,
+                                                      const double4* U, int64_t base, int width, const double4 u, int par,
+                                                      double& ax, double& ay, double& az) {
+  ax = 0.0; ay = 0.0; az = 0.0;
+  if (width <= 0) return;
+  int c[4]; double w2[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int64_t o = base + (int64_t)q * kSellC;
+    c[q] = __ldg(sell_col + o);
+    w2[q] = __ldg(sell_w2 + o);
+  }
+  for (int j = 0; j < width; j += 4) {
+    double4 uc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) uc[q] = ldcg256(U + c[q]);
+    int cn[4] = {0, 0, 0, 0}; double wn[4] = {0, 0, 0, 0};
+    if (j + 4 < width) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t o = base + (int64_t)(j + 4 + q) * kSellC;
+        cn[q] = __ldg(sell_col + o);
+        wn[q] = __ldg(sell_w2 + o);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (!has_tag(uc[q], par)) uc[q] = ld_tagged(U + c[q], par);          // not there yet: wait for this row only
+      ax += w2[q] * (u.x - uc[q].x); ay += w2[q] * (u.y - uc[q].y); az += w2[q] * (u.z - uc[q].z);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { c[q] = cn[q]; w2[q] = wn[q]; }
+  }
+}
+
+// Window layout of the LL variant: U | X | MR[2] | MS[2] | MW[2] (9 n double4), dots [2][kPeerMax][16] as
+// {value, epoch} pairs (2 doubles each -> [2][kPeerMax][32]), flags.
+struct PeerWindowLL {
+  double4 *U, *X, *MR[2], *MS[2], *MW[2];
+  double* dots;
+  unsigned long long* flags;
+};
+__host__ __device__ inline size_t peer_window_ll_bytes(int n) { return kPeerHdr + (size_t)9 * n * sizeof(double4); }
+__host__ __device__ inline PeerWindowLL peer_window_ll_at(unsigned char* base, int n) {
+  PeerWindowLL w;
+  double4* v = reinterpret_cast<double4*>(base + kPeerHdr);
+  w.U = v; w.X = v + (size_t)n;
+  w.MR[0] = v + (size_t)2 * n; w.MR[1] = v + (size_t)3 * n;
+  w.MS[0] = v + (size_t)4 * n; w.MS[1] = v + (size_t)5 * n;
+  w.MW[0] = v + (size_t)6 * n; w.MW[1] = v + (size_t)7 * n;
+  w.flags = reinterpret_cast<unsigned long long*>(base);
+  w.dots = reinterpret_cast<double*>(base + 256);
+  return w;
+}
+
+// fence-based barrier on the LL window (start and end of a solve only)
+__device__ __forceinline__ void peer_barrier_ll(const PcgPeerParams& q, cooperative_groups::grid_group& grid,
+                                                unsigned long long epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) __threadfence_system();
+  grid.sync();
+  if (blockIdx.x == 0 && threadIdx.x < q.world)
+    st_relaxed_sys(peer_window_ll_at(q.win[threadIdx.x], q.base.n).flags + q.rank, epoch);
+  if (threadIdx.x < q.world) {
+    const unsigned long long* f = peer_window_ll_at(q.win[q.rank], q.base.n).flags + threadIdx.x;
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
+    while (ld_relaxed_sys_u64(f) < epoch) {
+      if ((++spins & 0xfffu) == 0u) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 20000000000ull) asm volatile("trap;");
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kPeerThreads, 1)
+k_pcg_peer_ll(const PcgPeerParams q) {
+  namespace cgx = cooperative_groups;
+  const PcgParams& p = q.base;
+  cgx::grid_group grid = cgx::this_grid();
+  __shared__ double red[kPcgNV * 32];
+  __shared__ double tot[kPcgNV];
+  __shared__ double sc_bb[3], sc_go[3], sc_ao[3], sc_a[3], sc_b[3], sc_rr[3];
+  __shared__ int sc_stop;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = blockIdx.x + gridDim.x * (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const PeerWindowLL me = peer_window_ll_at(q.win[q.rank], p.n);
+  const bool has_pairs = p.npairs != nullptr && *p.npairs > 0;
+  unsigned long long epoch = q.epoch_base;
+  double v[kPcgNV];
+
+  // ---- start (replicated, local): u0 = M^-1 b for ALL rows with parity 0; block members' "previous"
+  //      (r, s) = (b, 0) with parity 1; own rows: x = 0, r = b, p = s = 0
+#pragma unroll
+  for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
+  for (int s = gwarp; s < p.nslices; s += nwarps) {
+    const int row = p.sell_row[s * kSellC + lane];
+    if (row >= 0) {
+      const double4 b = ldg256(p.B + row);
+      const double d = p.diag[row];
+      const double di = p.pc1 ? p.pc1[row] : (d > 0.0 ? 1.0 / d : 0.0);
+      double4 u0 = make_double4(di * b.x, di * b.y, di * b.z, 0.0);
+      if (has_pairs) {
+        const int mt = p.mate[row];
+        if (mt >= 0) {
+          const double4 bm = ldg256(p.B + mt);
+          const double c2 = p.pc2[row];
+          u0.x += c2 * bm.x; u0.y += c2 * bm.y; u0.z += c2 * bm.z;
+          const int m2 = p.mate2[row];
+          if (m2 >= 0) {
+            const double4 b2 = ldg256(p.B + m2);
+            const double c3 = p.pc3[row];
+            u0.x += c3 * b2.x; u0.y += c3 * b2.y; u0.z += c3 * b2.z;
+          }
+          // buffer k & 1 carries tag (k >> 1) & 1 for data of iteration k: the "previous" iteration -1 lives in
+          // buffer 1 with tag 1; every other buffer gets the tag its first writer will NOT use, so that stale
+          // rows of an earlier solve can never be mistaken for fresh ones
+          const double4 inval = tag4(0.0, 0.0, 0.0, 1);
+          st256(me.MR[1] + row, tag4(b.x, b.y, b.z, 1));
+          st256(me.MS[1] + row, inval);
+          st256(me.MR[0] + row, inval); st256(me.MS[0] + row, inval);
+          st256(me.MW[0] + row, inval); st256(me.MW[1] + row, inval);
+        }
+      }
+      st256(me.U + row, tag4(u0.x, u0.y, u0.z, 0));
+      if (s >= q.slice_lo && s < q.slice_hi) {
+        p.dinv[row] = di;
+        const double4 z4 = make_double4(0, 0, 0, 0);
+        st256(p.R + row, b); st256(p.P + row, z4); st256(p.S + row, z4); st256(me.X + row, z4);
+      }
+      v[0] += b.x * b.x; v[1] += b.y * b.y; v[2] += b.z * b.z;
+    }
+  }
+  pcg_grid_reduce(v, p.partials, grid, red, tot);
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < 3; ++c) { sc_bb[c] = v[c]; sc_rr[c] = v[c]; sc_go[c] = 1.0; sc_ao[c] = 1.0; }
+    sc_stop = !(v[0] > 0.0 || v[1] > 0.0 || v[2] > 0.0);
+  }
+  __syncthreads();
+  peer_barrier_ll(q, grid, ++epoch);       // nobody writes into a window before its owner initialised it
+  int it = 0;
+  const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+  long long c_spmv = 0, c_upd = 0, c_mark = 0, c_begin = 0;
+  unsigned long long ns_begin = 0;
+  if (timer) { c_begin = c_mark = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_begin)); }
+
+  while (!sc_stop) {
+    const int par = it & 1, old = par ^ 1;
+    const int tcur = (it >> 1) & 1, told = ((it - 1) >> 1) & 1;      // tags of this / the previous iteration's copies
+    // ---- phase A: w = A u on my rows (self-validating gathers), partial dots -------------------------
+#pragma unroll
+    for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
+    for (int s = q.slice_lo + gwarp; s < q.slice_hi; s += nwarps) {
+      const int row = p.sell_row[s * kSellC + lane];
+      const int width = p.slice_width[s];
+      const int64_t base = (int64_t)p.slice_off[s] + lane;
+      const double4 u = row >= 0 ? ld_tagged(me.U + row, par) : make_double4(0, 0, 0, 0);
+      double ax, ay, az;
+      sell_row_apply_tagged(p.sell_col, p.sell_w2, me.U, base, width, u, par, ax, ay, az);
+      if (row >= 0) {
+        st256(p.W + row, make_double4(ax, ay, az, 0.0));
+        if (has_pairs) {
+          const int mt = p.mate[row];
+          if (mt >= 0) {                                                   // my block mates need a copy of my w
+            const double4 wt = tag4(ax, ay, az, tcur);
+            const int o1 = peer_owner(q, mt);
+            st256(peer_window_ll_at(q.win[o1], p.n).MW[par] + row, wt);
+            const int m2 = p.mate2[row];
+            if (m2 >= 0) { const int o2 = peer_owner(q, m2); if (o2 != o1) st256(peer_window_ll_at(q.win[o2], p.n).MW[par] + row, wt); }
+          }
+        }
+        const double4 r = ld256(p.R + row);
+        v[0] += r.x * u.x; v[1] += r.y * u.y; v[2] += r.z * u.z;
+        v[3] += u.x * ax;  v[4] += u.y * ay;  v[5] += u.z * az;
+        v[6] += r.x * r.x; v[7] += r.y * r.y; v[8] += r.z * r.z;
+      }
+    }
+    pcg_grid_reduce(v, p.partials, grid, red, tot);        // rank-local block-ordered sum; the only grid barrier
+    ++epoch;
+    if (blockIdx.x == 0 && threadIdx.x < q.world * kPcgNV) {
+      const int g = threadIdx.x / kPcgNV, k = threadIdx.x % kPcgNV;
+      st_dot16(peer_window_ll_at(q.win[g], p.n).dots + ((par * kPeerMax + q.rank) * 16 + k) * 2, v[k], epoch);
+    }
+    if (threadIdx.x < kPcgNV) {
+      double t = 0.0;
+      for (int g = 0; g < q.world; ++g) t += ld_dot16(me.dots + ((par * kPeerMax + g) * 16 + threadIdx.x) * 2, epoch);
+      tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kPcgNV; ++k) v[k] = tot[k];
+    if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; }
+    if (threadIdx.x == 0) {
+      bool conv = true;
+      for (int c = 0; c < 3; ++c) {
+        sc_rr[c] = v[6 + c];
+        if (!(v[6 + c] <= p.rtol2 * sc_bb[c])) conv = false;
+      }
+      if (conv || it >= p.max_iters) {
+        sc_stop = 1;
+      } else {
+        for (int c = 0; c < 3; ++c) {
+          const double gam = v[c], del = v[3 + c];
+          double beta = 0.0, den = del;
+          if (it > 0) {
+            beta = sc_go[c] > 0.0 ? gam / sc_go[c] : 0.0;
+            if (sc_ao[c] != 0.0) den = del - beta * gam / sc_ao[c];
+          }
+          const double alpha = den > 0.0 ? gam / den : 0.0;
+          sc_go[c] = gam; sc_ao[c] = alpha; sc_a[c] = alpha; sc_b[c] = beta;
+        }
+      }
+    }
+    __syncthreads();
+    if (sc_stop) break;
+    const double a0 = sc_a[0], a1 = sc_a[1], a2 = sc_a[2], b0 = sc_b[0], b1 = sc_b[1], b2 = sc_b[2];
+    // ---- phase B: my rows of p, s, x, r, u; the new u (parity of the NEXT iteration) goes to every rank ----
+    const int nxt = old;                                   // (it + 1) & 1
+    for (int s = q.slice_lo + gwarp; s < q.slice_hi; s += nwarps) {
+      const int row = p.sell_row[s * kSellC + lane];
+      if (row >= 0) {
+        const double4 u = ldcg256(me.U + row), w = ld256(p.W + row);   // both written by this thread's own earlier phases
+        double4 pp = ld256(p.P + row), ss = ld256(p.S + row);
+        pp.x = u.x + b0 * pp.x; pp.y = u.y + b1 * pp.y; pp.z = u.z + b2 * pp.z;
+        ss.x = w.x + b0 * ss.x; ss.y = w.y + b1 * ss.y; ss.z = w.z + b2 * ss.z;
+        st256(p.P + row, pp); st256(p.S + row, ss);
+        double4 x = ld256(me.X + row), r = ld256(p.R + row);
+        const double di = p.dinv[row];
+        x.x += a0 * pp.x; x.y += a1 * pp.y; x.z += a2 * pp.z;
+        r.x -= a0 * ss.x; r.y -= a1 * ss.y; r.z -= a2 * ss.z;
+        st256(me.X + row, x); st256(p.R + row, r);
+        double ux = di * r.x, uy = di * r.y, uz = di * r.z;
+        if (has_pairs) {
+          const int mt = p.mate[row];
+          if (mt >= 0) {
+            // a mate's new residual from its previous (r, s) (parity `old`) and this iteration's w (parity `par`)
+            const double4 rm = ld_tagged(me.MR[old] + mt, told), sm = ld_tagged(me.MS[old] + mt, told);
+            const double4 wm = ld_tagged(me.MW[par] + mt, tcur);
+            const double c2 = p.pc2[row];
+            const double sm0 = wm.x + b0 * sm.x, sm1 = wm.y + b1 * sm.y, sm2 = wm.z + b2 * sm.z;
+            ux += c2 * (rm.x - a0 * sm0); uy += c2 * (rm.y - a1 * sm1); uz += c2 * (rm.z - a2 * sm2);
+            const double4 rt = tag4(r.x, r.y, r.z, tcur), st = tag4(ss.x, ss.y, ss.z, tcur);
+            const int o1 = peer_owner(q, mt);
+            const PeerWindowLL mw = peer_window_ll_at(q.win[o1], p.n);
+            st256(mw.MR[par] + row, rt);
+            st256(mw.MS[par] + row, st);
+            const int m2 = p.mate2[row];
+            if (m2 >= 0) {
+              const double4 rn = ld_tagged(me.MR[old] + m2, told), sn = ld_tagged(me.MS[old] + m2, told);
+              const double4 wn = ld_tagged(me.MW[par] + m2, tcur);
+              const double c3 = p.pc3[row];
+              const double t0 = wn.x + b0 * sn.x, t1 = wn.y + b1 * sn.y, t2 = wn.z + b2 * sn.z;
+              ux += c3 * (rn.x - a0 * t0); uy += c3 * (rn.y - a1 * t1); uz += c3 * (rn.z - a2 * t2);
+              const int o2 = peer_owner(q, m2);
+              if (o2 != o1) {
+                const PeerWindowLL mw2 = peer_window_ll_at(q.win[o2], p.n);
+                st256(mw2.MR[par] + row, rt);
+                st256(mw2.MS[par] + row, st);
+              }
+            }
+          }
+        }
+        const double4 un = tag4(ux, uy, uz, nxt);
+#pragma unroll
+        for (int g = 0; g < kPeerMax; ++g)
+          if (g < q.world) st256(reinterpret_cast<double4*>(q.win[g] + kPeerHdr) + row, un);   // U is the first vector
+      }
+    }
+    ++it;
+    if (timer) { const long long c = clock64(); c_upd += c - c_mark; c_mark = c; }
+  }
+  // ---- all-gather of the solution ----------------------------------------------------------------------
+  for (int s = q.slice_lo + gwarp; s < q.slice_hi; s += nwarps) {
+    const int row = p.sell_row[s * kSellC + lane];
+    if (row >= 0) {
+      const double4 x = ld256(me.X + row);
+      for (int g = 0; g < q.world; ++g)
+        if (g != q.rank) st256(peer_window_ll_at(q.win[g], p.n).X + row, x);
+    }
+  }
+  peer_barrier_ll(q, grid, ++epoch);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     p.ctl->epoch = epoch;
     p.ctl->cg_iters = it;

@@ -55,7 +55,7 @@ PEER_WORKER = textwrap.dedent("""
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     sigma = 5 * np.pi / 180
-    s = ira.Solver(device=lr, world_size=world, rank=rank, shard_mode=1)
+    s = ira.Solver(device=lr, world_size=world, rank=rank, shard_mode=int(os.environ["IRA_SHARD_MODE"]))
     s.comm_init(broadcast_unique_id(dist, ira.Solver, rank, device="cuda"))
     ref = np.load(os.environ["IRA_REF"])                # oracle results computed once by the parent process
     ok = True
@@ -93,9 +93,11 @@ def _torchrun(tmp_path, text, nproc, timeout=900, extra_env=None):
     return subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
 
 
-def test_peer_memory_solve(tmp_path, built_lib):
-    """shard_mode 1: rows partitioned over the ranks, one persistent kernel per rank, exchange through NVLink peer
-    memory (ira_peer.cuh).  Every rank holds the whole graph; results must match the oracle and each other bitwise."""
+@pytest.mark.parametrize("shard_mode", [1, 2])
+def test_peer_memory_solve(tmp_path, built_lib, shard_mode):
+    """shard_mode 1 / 2: rows partitioned over the ranks, one persistent kernel per rank, exchange through NVLink peer
+    memory (ira_peer.cuh; 1 = barrier-free with self-validating data, 2 = two cross-GPU barriers per iteration).
+    Every rank holds the whole graph; results must match the oracle and each other bitwise."""
     import irotavg_b200 as ira
     import numpy as np
     from oracle import graphs as G, irls_oracle as O
@@ -112,7 +114,8 @@ def test_peer_memory_solve(tmp_path, built_lib):
             ref[f"Q_{gi}_{cost}"], ref[f"w_{gi}_{cost}"] = r.Q, r.weights
     np.savez(tmp_path / "ref.npz", **ref)
     res = _torchrun(tmp_path, PEER_WORKER, min(nd, 8) if nd in (2, 4, 8) else 2,
-                    extra_env={"IRA_REF": str(tmp_path / "ref.npz"), "IRA_GRAPHS": repr(PEER_GRAPHS)})
+                    extra_env={"IRA_REF": str(tmp_path / "ref.npz"), "IRA_GRAPHS": repr(PEER_GRAPHS),
+                               "IRA_SHARD_MODE": str(shard_mode)})
     print(res.stdout[-3000:])
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
 

@@ -17,7 +17,8 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 sigma = 5 * np.pi / 180
 variant = int(os.environ.get("IRA_SPMV_VARIANT", "0"))
-s = ira.Solver(device=lr, world_size=world, rank=rank, shard_mode=1, spmv_variant=variant)
+mode = int(os.environ.get("IRA_SHARD_MODE", "1"))      # 1 = barrier-free exchange, 2 = two cross-GPU barriers per iteration
+s = ira.Solver(device=lr, world_size=world, rank=rank, shard_mode=mode, spmv_variant=variant)
 s.comm_init(broadcast_unique_id(dist, ira.Solver, rank, device="cuda"))
 for name, g in (("tiny n=3000", G.small_graph(n=3000, extra=30000, sigma_n=0.03, outlier_frac=0.1, seed=41)),
                 ("config 3", G.random_graph())):
@@ -29,7 +30,7 @@ for name, g in (("tiny n=3000", G.small_graph(n=3000, extra=30000, sigma_n=0.03,
         ph = info.profile["pcg_phases"]
         n_it = sum(info.cg_iters)
         if rank == 0:
-            print(f"{name} cost {cost}: cg {n_it} kernel {ph['kernel_ms']:.2f} ms -> {1e3 * ph['kernel_ms'] / max(n_it, 1):.1f} us/iter; "
+            print(f"[shard_mode {mode}, {world} ranks] {name} cost {cost}: cg {n_it} kernel {ph['kernel_ms']:.2f} ms -> {1e3 * ph['kernel_ms'] / max(n_it, 1):.1f} us/iter; "
                   f"phase A (SpMV+dots+barrier) {1e3 * ph['spmv_ms'] / max(ph['spmv_phases'], 1):.1f} us, "
                   f"phase B (update+all-gather+barrier) {1e3 * ph['update_ms'] / max(n_it, 1):.1f} us", flush=True)
 s.close()
