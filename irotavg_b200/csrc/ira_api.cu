@@ -117,7 +117,7 @@ struct ira_context {
   ncclComm_t comm = nullptr;
   // peer-memory solve (ira_peer.cuh): this rank's window, the peers' windows mapped through CUDA IPC
   bool peer = false;
-  DevBuf peer_win, sell_pos, ipc_stage;
+  DevBuf peer_win, sell_pos, ipc_stage, sell_colpos;
   void* peer_mapped[kPeerMax] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void* peer_exported = nullptr;        // the window address the current mappings were exchanged for
   int peer_n = 0;
@@ -500,7 +500,8 @@ ira_status peer_setup(ira_context* h) {
   if (G > kPeerMax) { h->err = "peer-memory solve supports at most 8 ranks"; return IRA_ERR_INVALID_ARG; }
   if (!h->comm) { h->err = "world_size > 1 but ira_comm_init was not called"; return IRA_ERR_COMM; }
   void* before = h->peer_win.p;
-  IRA_CUDA(h, h->peer_win.reserve(std::max(peer_window_bytes(n), peer_window_ll_bytes(n))));
+  IRA_CUDA(h, h->peer_win.reserve(std::max(peer_window_bytes(n), peer_window_ll_bytes(std::max(h->npos, 1)))));
+  IRA_CUDA(h, h->sell_colpos.reserve(sizeof(int) * (size_t)std::max<int64_t>(h->sell_total, 1)));
   // every rank takes the same decision: all see the same n, and a window only ever grows
   if (h->peer_win.p != before || h->peer_exported != h->peer_win.p) {
     for (int g = 0; g < kPeerMax; ++g)
@@ -536,6 +537,9 @@ ira_status peer_setup(ira_context* h) {
     IRA_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   h->peer_n = n;
+  k_sell_colpos<<<std::max(1, std::min(cdiv(std::max<int64_t>(h->sell_total, 1), 256), h->sms * 8)), 256, 0, h->stream>>>(
+      h->sell_col.as<int>(), h->sell_pos.as<int>(), h->sell_total, h->sell_colpos.as<int>());
+  IRA_TRY(launch_check(h, "k_sell_colpos"));
   if (h->peer_blocks_per_sm == 0) {
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_peer<0, 4>, kPeerThreads, 0) != cudaSuccess || nb < 1) {
@@ -577,6 +581,9 @@ ira_status solve_pcg_peer(ira_context* h) {
   q.sell_pos = h->sell_pos.as<int>();
   for (int g = 0; g < G; ++g) q.win[g] = (unsigned char*)(g == q.rank ? h->peer_win.p : h->peer_mapped[g]);
   q.epoch_base = h->peer_epoch;
+  q.debug = h->opt.spmv_variant == 7;
+  q.sell_colpos = h->sell_colpos.as<int>();
+  q.npos = h->npos;
   const int own = std::max(1, q.slice_hi - q.slice_lo);
   const int grid = std::max(1, std::min(own, h->sms * h->peer_blocks_per_sm));
   ProfScope ps(h, KC_PCG);
@@ -585,8 +592,9 @@ ira_status solve_pcg_peer(ira_context* h) {
   void* fn = ll ? (void*)k_pcg_peer_ll : (h->opt.spmv_variant == 1 ? (void*)k_pcg_peer<1, 4> : (void*)k_pcg_peer<0, 4>);
   IRA_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPeerThreads), args, 0, h->stream));
   h->launches++;
-  const PeerWindow me = peer_window_at((unsigned char*)h->peer_win.p, h->peer_n);   // X sits at the same offset in both layouts
-  IRA_CUDA(h, cudaMemcpyAsync(h->X.p, me.X, sizeof(double4) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
+  const double4* xsrc = ll ? peer_window_ll_at((unsigned char*)h->peer_win.p, h->npos).X
+                           : peer_window_at((unsigned char*)h->peer_win.p, h->peer_n).X;
+  IRA_CUDA(h, cudaMemcpyAsync(h->X.p, xsrc, sizeof(double4) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
   return IRA_OK;
 }
 
@@ -859,7 +867,7 @@ ira_status ira_destroy(ira_handle h) {
                     &h->R2, &h->S2, &h->pdU, &h->pdAX, &h->pdL1, &h->pdL2, &h->pdADX, &h->pdDU, &h->pdDL1, &h->pdDL2, &h->pdEV,
                     &h->pdSIGX, &h->sell_w3, &h->pdX, &h->pdATV, &h->pdATDV, &h->pdW1P, &h->pdDX, &h->diag3, &h->dinv3,
                     &h->pdctl, &h->pdtrial, &h->mst_label, &h->mst_label2, &h->mst_order, &h->mst_order2, &h->mst_done,
-                    &h->mst_ctl, &h->sell_pos, &h->ipc_stage, &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs, &h->mate2, &h->pc3, &h->att_key})
+                    &h->mst_ctl, &h->sell_pos, &h->ipc_stage, &h->sell_colpos, &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs, &h->mate2, &h->pc3, &h->att_key})
     b->release();
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);

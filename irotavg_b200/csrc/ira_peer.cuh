@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "ira_pcg.cuh"
 #include "ira_mst.cuh"      // ldcg256
@@ -61,6 +62,9 @@ struct PcgPeerParams {
   int slice_bound[kPeerMax + 1];
   unsigned char* win[kPeerMax];   // window base of every rank in THIS process's address space (own: local)
   unsigned long long epoch_base;  // flags hold monotonically increasing epochs across launches
+  int debug;                      // print block 0's phase split (spmv_variant 7)
+  const int* sell_colpos;         // LL variant: SELL slot -> POSITION of its column (u lives in position order there)
+  int npos;                       // padded row count (vector stride of the LL window)
 };
 
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
@@ -448,7 +452,7 @@ struct PeerWindowLL {
   double* dots;
   unsigned long long* flags;
 };
-__host__ __device__ inline size_t peer_window_ll_bytes(int n) { return kPeerHdr + (size_t)9 * n * sizeof(double4); }
+__host__ __device__ inline size_t peer_window_ll_bytes(int npos) { return kPeerHdr + (size_t)9 * npos * sizeof(double4); }
 __host__ __device__ inline PeerWindowLL peer_window_ll_at(unsigned char* base, int n) {
   PeerWindowLL w;
   double4* v = reinterpret_cast<double4*>(base + kPeerHdr);
@@ -498,7 +502,7 @@ k_pcg_peer_ll(const PcgPeerParams q) {
   const int lane = threadIdx.x & 31;
   const int gwarp = blockIdx.x + gridDim.x * (threadIdx.x >> 5);
   const int nwarps = gridDim.x * (blockDim.x >> 5);
-  const PeerWindowLL me = peer_window_ll_at(q.win[q.rank], p.n);
+  const PeerWindowLL me = peer_window_ll_at(q.win[q.rank], q.npos);
   const bool has_pairs = p.npairs != nullptr && *p.npairs > 0;
   unsigned long long epoch = q.epoch_base;
   double v[kPcgNV];
@@ -536,7 +540,7 @@ k_pcg_peer_ll(const PcgPeerParams q) {
           st256(me.MW[0] + row, inval); st256(me.MW[1] + row, inval);
         }
       }
-      st256(me.U + row, tag4(u0.x, u0.y, u0.z, 0));
+      st256(me.U + (s * kSellC + lane), tag4(u0.x, u0.y, u0.z, 0));   // u lives in SELL-position order: a warp's 32 rows are 1 KB contiguous
       if (s >= q.slice_lo && s < q.slice_hi) {
         p.dinv[row] = di;
         const double4 z4 = make_double4(0, 0, 0, 0);
@@ -555,6 +559,7 @@ k_pcg_peer_ll(const PcgPeerParams q) {
   int it = 0;
   const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
   long long c_spmv = 0, c_upd = 0, c_mark = 0, c_begin = 0;
+  long long d_mv = 0, d_red = 0, d_dot = 0, d_t = 0;      // debug split of phase A (q.debug)
   unsigned long long ns_begin = 0;
   if (timer) { c_begin = c_mark = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_begin)); }
 
@@ -568,9 +573,9 @@ k_pcg_peer_ll(const PcgPeerParams q) {
       const int row = p.sell_row[s * kSellC + lane];
       const int width = p.slice_width[s];
       const int64_t base = (int64_t)p.slice_off[s] + lane;
-      const double4 u = row >= 0 ? ld_tagged(me.U + row, par) : make_double4(0, 0, 0, 0);
+      const double4 u = row >= 0 ? ld_tagged(me.U + (s * kSellC + lane), par) : make_double4(0, 0, 0, 0);
       double ax, ay, az;
-      sell_row_apply_tagged(p.sell_col, p.sell_w2, me.U, base, width, u, par, ax, ay, az);
+      sell_row_apply_tagged(q.sell_colpos, p.sell_w2, me.U, base, width, u, par, ax, ay, az);
       if (row >= 0) {
         st256(p.W + row, make_double4(ax, ay, az, 0.0));
         if (has_pairs) {
@@ -578,9 +583,9 @@ k_pcg_peer_ll(const PcgPeerParams q) {
           if (mt >= 0) {                                                   // my block mates need a copy of my w
             const double4 wt = tag4(ax, ay, az, tcur);
             const int o1 = peer_owner(q, mt);
-            st256(peer_window_ll_at(q.win[o1], p.n).MW[par] + row, wt);
+            st256(peer_window_ll_at(q.win[o1], q.npos).MW[par] + row, wt);
             const int m2 = p.mate2[row];
-            if (m2 >= 0) { const int o2 = peer_owner(q, m2); if (o2 != o1) st256(peer_window_ll_at(q.win[o2], p.n).MW[par] + row, wt); }
+            if (m2 >= 0) { const int o2 = peer_owner(q, m2); if (o2 != o1) st256(peer_window_ll_at(q.win[o2], q.npos).MW[par] + row, wt); }
           }
         }
         const double4 r = ld256(p.R + row);
@@ -589,11 +594,13 @@ k_pcg_peer_ll(const PcgPeerParams q) {
         v[6] += r.x * r.x; v[7] += r.y * r.y; v[8] += r.z * r.z;
       }
     }
+    if (timer) { d_t = clock64(); d_mv += d_t - c_mark; }
     pcg_grid_reduce(v, p.partials, grid, red, tot);        // rank-local block-ordered sum; the only grid barrier
+    if (timer) { const long long c = clock64(); d_red += c - d_t; d_t = c; }
     ++epoch;
     if (blockIdx.x == 0 && threadIdx.x < q.world * kPcgNV) {
       const int g = threadIdx.x / kPcgNV, k = threadIdx.x % kPcgNV;
-      st_dot16(peer_window_ll_at(q.win[g], p.n).dots + ((par * kPeerMax + q.rank) * 16 + k) * 2, v[k], epoch);
+      st_dot16(peer_window_ll_at(q.win[g], q.npos).dots + ((par * kPeerMax + q.rank) * 16 + k) * 2, v[k], epoch);
     }
     if (threadIdx.x < kPcgNV) {
       double t = 0.0;
@@ -603,7 +610,7 @@ k_pcg_peer_ll(const PcgPeerParams q) {
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kPcgNV; ++k) v[k] = tot[k];
-    if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; }
+    if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; d_dot += c - d_t; }
     if (threadIdx.x == 0) {
       bool conv = true;
       for (int c = 0; c < 3; ++c) {
@@ -633,7 +640,7 @@ k_pcg_peer_ll(const PcgPeerParams q) {
     for (int s = q.slice_lo + gwarp; s < q.slice_hi; s += nwarps) {
       const int row = p.sell_row[s * kSellC + lane];
       if (row >= 0) {
-        const double4 u = ldcg256(me.U + row), w = ld256(p.W + row);   // both written by this thread's own earlier phases
+        const double4 u = ldcg256(me.U + (s * kSellC + lane)), w = ld256(p.W + row);   // both written by this thread's own earlier phases
         double4 pp = ld256(p.P + row), ss = ld256(p.S + row);
         pp.x = u.x + b0 * pp.x; pp.y = u.y + b1 * pp.y; pp.z = u.z + b2 * pp.z;
         ss.x = w.x + b0 * ss.x; ss.y = w.y + b1 * ss.y; ss.z = w.z + b2 * ss.z;
@@ -648,26 +655,32 @@ k_pcg_peer_ll(const PcgPeerParams q) {
           const int mt = p.mate[row];
           if (mt >= 0) {
             // a mate's new residual from its previous (r, s) (parity `old`) and this iteration's w (parity `par`)
-            const double4 rm = ld_tagged(me.MR[old] + mt, told), sm = ld_tagged(me.MS[old] + mt, told);
-            const double4 wm = ld_tagged(me.MW[par] + mt, tcur);
+            // issue every load first, validate afterwards: one L2 round trip instead of up to six in a row
+            const int m2 = p.mate2[row];
+            double4 rm = ldcg256(me.MR[old] + mt), sm = ldcg256(me.MS[old] + mt), wm = ldcg256(me.MW[par] + mt);
+            double4 rn = make_double4(0, 0, 0, 0), sn = rn, wn = rn;
+            if (m2 >= 0) { rn = ldcg256(me.MR[old] + m2); sn = ldcg256(me.MS[old] + m2); wn = ldcg256(me.MW[par] + m2); }
+            if (!has_tag(rm, told)) rm = ld_tagged(me.MR[old] + mt, told);
+            if (!has_tag(sm, told)) sm = ld_tagged(me.MS[old] + mt, told);
+            if (!has_tag(wm, tcur)) wm = ld_tagged(me.MW[par] + mt, tcur);
             const double c2 = p.pc2[row];
             const double sm0 = wm.x + b0 * sm.x, sm1 = wm.y + b1 * sm.y, sm2 = wm.z + b2 * sm.z;
             ux += c2 * (rm.x - a0 * sm0); uy += c2 * (rm.y - a1 * sm1); uz += c2 * (rm.z - a2 * sm2);
             const double4 rt = tag4(r.x, r.y, r.z, tcur), st = tag4(ss.x, ss.y, ss.z, tcur);
             const int o1 = peer_owner(q, mt);
-            const PeerWindowLL mw = peer_window_ll_at(q.win[o1], p.n);
+            const PeerWindowLL mw = peer_window_ll_at(q.win[o1], q.npos);
             st256(mw.MR[par] + row, rt);
             st256(mw.MS[par] + row, st);
-            const int m2 = p.mate2[row];
             if (m2 >= 0) {
-              const double4 rn = ld_tagged(me.MR[old] + m2, told), sn = ld_tagged(me.MS[old] + m2, told);
-              const double4 wn = ld_tagged(me.MW[par] + m2, tcur);
+              if (!has_tag(rn, told)) rn = ld_tagged(me.MR[old] + m2, told);
+              if (!has_tag(sn, told)) sn = ld_tagged(me.MS[old] + m2, told);
+              if (!has_tag(wn, tcur)) wn = ld_tagged(me.MW[par] + m2, tcur);
               const double c3 = p.pc3[row];
               const double t0 = wn.x + b0 * sn.x, t1 = wn.y + b1 * sn.y, t2 = wn.z + b2 * sn.z;
               ux += c3 * (rn.x - a0 * t0); uy += c3 * (rn.y - a1 * t1); uz += c3 * (rn.z - a2 * t2);
               const int o2 = peer_owner(q, m2);
               if (o2 != o1) {
-                const PeerWindowLL mw2 = peer_window_ll_at(q.win[o2], p.n);
+                const PeerWindowLL mw2 = peer_window_ll_at(q.win[o2], q.npos);
                 st256(mw2.MR[par] + row, rt);
                 st256(mw2.MS[par] + row, st);
               }
@@ -676,8 +689,8 @@ k_pcg_peer_ll(const PcgPeerParams q) {
         }
         const double4 un = tag4(ux, uy, uz, nxt);
 #pragma unroll
-        for (int g = 0; g < kPeerMax; ++g)
-          if (g < q.world) st256(reinterpret_cast<double4*>(q.win[g] + kPeerHdr) + row, un);   // U is the first vector
+        for (int g = 0; g < kPeerMax; ++g)                 // 32 lanes x 32 B contiguous per destination: full NVLink packets
+          if (g < q.world) st256(reinterpret_cast<double4*>(q.win[g] + kPeerHdr) + (s * kSellC + lane), un);   // U is the first vector
       }
     }
     ++it;
@@ -689,7 +702,7 @@ k_pcg_peer_ll(const PcgPeerParams q) {
     if (row >= 0) {
       const double4 x = ld256(me.X + row);
       for (int g = 0; g < q.world; ++g)
-        if (g != q.rank) st256(peer_window_ll_at(q.win[g], p.n).X + row, x);
+        if (g != q.rank) st256(peer_window_ll_at(q.win[g], q.npos).X + row, x);
     }
   }
   peer_barrier_ll(q, grid, ++epoch);
@@ -705,7 +718,17 @@ k_pcg_peer_ll(const PcgPeerParams q) {
     p.ctl->cyc_total += clock64() - c_begin;
     p.ctl->ns_total += (long long)(ns_end - ns_begin);
     p.ctl->pcg_spmv_phases += c_spmv > 0 ? it + 1 : 0;
+    if (q.debug && q.rank == 0)
+      printf("[k_pcg_peer_ll] iters %d: cycles/iter SpMV %lld, local reduce %lld, dot exchange %lld, update %lld\n", it,
+             d_mv / (it + 1), d_red / (it + 1), d_dot / (it + 1), c_upd / (it > 0 ? it : 1));
   }
+}
+
+// SELL slot -> position of its column
+__global__ void k_sell_colpos(const int* __restrict__ sell_col, const int* __restrict__ sell_pos, int64_t total,
+                              int* __restrict__ colpos) {
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x)
+    colpos[o] = sell_pos[sell_col[o]];
 }
 
 // row -> SELL position
