@@ -581,16 +581,29 @@ ira_status solve_pcg_peer(ira_context* h) {
   q.sell_pos = h->sell_pos.as<int>();
   for (int g = 0; g < G; ++g) q.win[g] = (unsigned char*)(g == q.rank ? h->peer_win.p : h->peer_mapped[g]);
   q.epoch_base = h->peer_epoch;
-  q.debug = h->opt.spmv_variant == 7;
+  q.debug = (h->opt.spmv_variant & 7) == 7;
+  { const int fv = (h->opt.spmv_variant >> 3) & 3; q.flush = fv == 0 ? 1 : fv - 1; }   // default: one fence per warp
   q.sell_colpos = h->sell_colpos.as<int>();
   q.npos = h->npos;
   const int own = std::max(1, q.slice_hi - q.slice_lo);
-  const int grid = std::max(1, std::min(own, h->sms * h->peer_blocks_per_sm));
+  int grid = std::max(1, std::min(own, h->sms * h->peer_blocks_per_sm));
   ProfScope ps(h, KC_PCG);
   void* args[] = {(void*)&q};
   const bool ll = h->opt.shard_mode == 1;                // 2 = the barrier version (A/B measurements)
   void* fn = ll ? (void*)k_pcg_peer_ll : (h->opt.spmv_variant == 1 ? (void*)k_pcg_peer<1, 4> : (void*)k_pcg_peer<0, 4>);
-  IRA_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPeerThreads), args, 0, h->stream));
+  int threads = kPeerThreads;
+  // one row per lane fits (on EVERY rank: the largest slice range decides, so all ranks take the same kernel)
+  int max_own = 0;
+  for (int g = 0; g < G; ++g) max_own = std::max(max_own, q.slice_bound[g + 1] - q.slice_bound[g]);
+  if (ll && !(h->opt.solver & 4) && h->pcg_blocks_per_sm >= 1 && max_own <= h->sms * (kPcgThreads / 32)) {
+    fn = (void*)k_pcg_peer_ll_reg;
+    threads = kPcgThreads;
+    grid = std::max(1, std::min(h->sms, cdiv(max_own, kPcgThreads / 32)));
+    // slices are dealt round-robin over the blocks: slice = lo + block + grid * warp must cover [lo, hi)
+    grid = std::max(grid, std::min(h->sms, max_own));
+    if ((int64_t)grid * (kPcgThreads / 32) < max_own) { fn = (void*)k_pcg_peer_ll; threads = kPeerThreads; grid = std::max(1, std::min(own, h->sms * h->peer_blocks_per_sm)); }
+  }
+  IRA_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, 0, h->stream));
   h->launches++;
   const double4* xsrc = ll ? peer_window_ll_at((unsigned char*)h->peer_win.p, h->npos).X
                            : peer_window_at((unsigned char*)h->peer_win.p, h->peer_n).X;

@@ -62,7 +62,10 @@ struct PcgPeerParams {
   int slice_bound[kPeerMax + 1];
   unsigned char* win[kPeerMax];   // window base of every rank in THIS process's address space (own: local)
   unsigned long long epoch_base;  // flags hold monotonically increasing epochs across launches
-  int debug;                      // print block 0's phase split (spmv_variant 7)
+  int debug;                      // print block 0's phase split (spmv_variant & 7 == 7)
+  int flush;                      // 1 (default) = one system fence per warp after the u stores: pushes them onto the
+                                  // link at once (NVLink store completion ~7 us here; -5 us per iteration measured),
+                                  // 0 = none, 2 = one per block (spmv_variant bits 3-4, experiments)
   const int* sell_colpos;         // LL variant: SELL slot -> POSITION of its column (u lives in position order there)
   int npos;                       // padded row count (vector stride of the LL window)
 };
@@ -720,6 +723,233 @@ k_pcg_peer_ll(const PcgPeerParams q) {
     p.ctl->pcg_spmv_phases += c_spmv > 0 ? it + 1 : 0;
     if (q.debug && q.rank == 0)
       printf("[k_pcg_peer_ll] iters %d: cycles/iter SpMV %lld, local reduce %lld, dot exchange %lld, update %lld\n", it,
+             d_mv / (it + 1), d_red / (it + 1), d_dot / (it + 1), c_upd / (it > 0 ? it : 1));
+  }
+}
+
+// Register-resident form of the barrier-free kernel: when a rank's slices fit one per warp (rows per rank <=
+// grid x warps x 32), every lane owns ONE row for the whole solve and keeps x, r, p, s, u and its block
+// coefficients in registers, like k_pcg_persistent_reg.  The vector update then touches memory only to publish
+// the new u (and the block copies): the 13 x 32 B per row of L2 traffic of the HBM-resident form - which is what
+// bounded its update phase (6 us for 50 000 rows, tools/peer_probe.py) - disappear.
+__global__ void __launch_bounds__(kPcgThreads, 1)
+k_pcg_peer_ll_reg(const PcgPeerParams q) {
+  namespace cgx = cooperative_groups;
+  const PcgParams& p = q.base;
+  cgx::grid_group grid = cgx::this_grid();
+  __shared__ double red[kPcgNV * 32];
+  __shared__ double tot[kPcgNV];
+  __shared__ double sc_bb[3], sc_go[3], sc_ao[3], sc_a[3], sc_b[3], sc_rr[3];
+  __shared__ int sc_stop;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = blockIdx.x + gridDim.x * (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const PeerWindowLL me = peer_window_ll_at(q.win[q.rank], q.npos);
+  const bool has_pairs = p.npairs != nullptr && *p.npairs > 0;
+  unsigned long long epoch = q.epoch_base;
+  double v[kPcgNV];
+
+  // ---- start, replicated and local (same as k_pcg_peer_ll): tagged u0 of ALL rows, block rows' buffers ----
+#pragma unroll
+  for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
+  for (int s = gwarp; s < p.nslices; s += nwarps) {
+    const int row = p.sell_row[s * kSellC + lane];
+    if (row >= 0) {
+      const double4 b = ldg256(p.B + row);
+      const double d = p.diag[row];
+      const double di = p.pc1 ? p.pc1[row] : (d > 0.0 ? 1.0 / d : 0.0);
+      double4 u0 = make_double4(di * b.x, di * b.y, di * b.z, 0.0);
+      if (has_pairs) {
+        const int mt = p.mate[row];
+        if (mt >= 0) {
+          const double4 bm = ldg256(p.B + mt);
+          const double c2 = p.pc2[row];
+          u0.x += c2 * bm.x; u0.y += c2 * bm.y; u0.z += c2 * bm.z;
+          const int m2 = p.mate2[row];
+          if (m2 >= 0) {
+            const double4 b2 = ldg256(p.B + m2);
+            const double c3 = p.pc3[row];
+            u0.x += c3 * b2.x; u0.y += c3 * b2.y; u0.z += c3 * b2.z;
+          }
+          const double4 inval = tag4(0.0, 0.0, 0.0, 1);
+          st256(me.MR[1] + row, tag4(b.x, b.y, b.z, 1));
+          st256(me.MS[1] + row, inval);
+          st256(me.MR[0] + row, inval); st256(me.MS[0] + row, inval);
+          st256(me.MW[0] + row, inval); st256(me.MW[1] + row, inval);
+        }
+      }
+      st256(me.U + (s * kSellC + lane), tag4(u0.x, u0.y, u0.z, 0));
+      v[0] += b.x * b.x; v[1] += b.y * b.y; v[2] += b.z * b.z;
+    }
+  }
+  pcg_grid_reduce(v, p.partials, grid, red, tot);
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < 3; ++c) { sc_bb[c] = v[c]; sc_rr[c] = v[c]; sc_go[c] = 1.0; sc_ao[c] = 1.0; }
+    sc_stop = !(v[0] > 0.0 || v[1] > 0.0 || v[2] > 0.0);
+  }
+  __syncthreads();
+  peer_barrier_ll(q, grid, ++epoch);
+
+  // ---- this lane's row -------------------------------------------------------------------------------
+  const int slice = q.slice_lo + gwarp;                    // <= 1 slice per warp (checked by the host)
+  int row = -1, width = 0, mt = -1, mt2 = -1, o1 = 0, o2 = 0, pos = 0;
+  int64_t base = 0;
+  double x0 = 0, x1 = 0, x2 = 0, r0 = 0, r1 = 0, r2 = 0, p0 = 0, p1 = 0, p2 = 0, s0 = 0, s1 = 0, s2 = 0;
+  double u0 = 0, u1 = 0, u2 = 0, di = 0, c2 = 0, c3 = 0;
+  if (slice < q.slice_hi) {
+    pos = slice * kSellC + lane;
+    row = p.sell_row[pos];
+    width = p.slice_width[slice];
+    base = (int64_t)p.slice_off[slice] + lane;
+  }
+  if (row >= 0) {
+    const double4 b = ldg256(p.B + row);
+    const double d = p.diag[row];
+    di = p.pc1 ? p.pc1[row] : (d > 0.0 ? 1.0 / d : 0.0);
+    r0 = b.x; r1 = b.y; r2 = b.z;
+    const double4 ut = ldcg256(me.U + pos);                // the tagged value everybody else will gather
+    u0 = ut.x; u1 = ut.y; u2 = ut.z;
+    if (has_pairs) {
+      mt = p.mate[row];
+      if (mt >= 0) {
+        c2 = p.pc2[row];
+        o1 = peer_owner(q, mt);
+        mt2 = p.mate2[row];
+        if (mt2 >= 0) { c3 = p.pc3[row]; o2 = peer_owner(q, mt2); }
+      }
+    }
+  }
+  int it = 0;
+  const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+  long long c_spmv = 0, c_upd = 0, c_mark = 0, c_begin = 0;
+  long long d_mv = 0, d_red = 0, d_dot = 0, d_t = 0;
+  unsigned long long ns_begin = 0;
+  if (timer) { c_begin = c_mark = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_begin)); }
+
+  while (!sc_stop) {
+    const int par = it & 1, old = par ^ 1;
+    const int tcur = (it >> 1) & 1, told = ((it - 1) >> 1) & 1;
+    // ---- phase A ----
+    double w0 = 0, w1 = 0, w2 = 0;
+    if (row >= 0 || width > 0)
+      sell_row_apply_tagged(q.sell_colpos, p.sell_w2, me.U, base, width, make_double4(u0, u1, u2, 0.0), par, w0, w1, w2);
+    if (row >= 0) {
+      if (mt >= 0) {
+        const double4 wt = tag4(w0, w1, w2, tcur);
+        st256(peer_window_ll_at(q.win[o1], q.npos).MW[par] + row, wt);
+        if (mt2 >= 0 && o2 != o1) st256(peer_window_ll_at(q.win[o2], q.npos).MW[par] + row, wt);
+      }
+      v[0] = r0 * u0; v[1] = r1 * u1; v[2] = r2 * u2;
+      v[3] = u0 * w0; v[4] = u1 * w1; v[5] = u2 * w2;
+      v[6] = r0 * r0; v[7] = r1 * r1; v[8] = r2 * r2;
+    } else {
+#pragma unroll
+      for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
+    }
+    if (timer) { d_t = clock64(); d_mv += d_t - c_mark; }
+    pcg_grid_reduce(v, p.partials, grid, red, tot);
+    if (timer) { const long long c = clock64(); d_red += c - d_t; d_t = c; }
+    ++epoch;
+    if (blockIdx.x == 0 && threadIdx.x < q.world * kPcgNV) {
+      const int g = threadIdx.x / kPcgNV, k = threadIdx.x % kPcgNV;
+      st_dot16(peer_window_ll_at(q.win[g], q.npos).dots + ((par * kPeerMax + q.rank) * 16 + k) * 2, v[k], epoch);
+    }
+    if (threadIdx.x < kPcgNV) {
+      double t = 0.0;
+      for (int g = 0; g < q.world; ++g) t += ld_dot16(me.dots + ((par * kPeerMax + g) * 16 + threadIdx.x) * 2, epoch);
+      tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kPcgNV; ++k) v[k] = tot[k];
+    if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; d_dot += c - d_t; }
+    if (threadIdx.x == 0) {
+      bool conv = true;
+      for (int c = 0; c < 3; ++c) {
+        sc_rr[c] = v[6 + c];
+        if (!(v[6 + c] <= p.rtol2 * sc_bb[c])) conv = false;
+      }
+      if (conv || it >= p.max_iters) {
+        sc_stop = 1;
+      } else {
+        for (int c = 0; c < 3; ++c) {
+          const double gam = v[c], del = v[3 + c];
+          double beta = 0.0, den = del;
+          if (it > 0) {
+            beta = sc_go[c] > 0.0 ? gam / sc_go[c] : 0.0;
+            if (sc_ao[c] != 0.0) den = del - beta * gam / sc_ao[c];
+          }
+          const double alpha = den > 0.0 ? gam / den : 0.0;
+          sc_go[c] = gam; sc_ao[c] = alpha; sc_a[c] = alpha; sc_b[c] = beta;
+        }
+      }
+    }
+    __syncthreads();
+    if (sc_stop) break;
+    const double a0 = sc_a[0], a1 = sc_a[1], a2 = sc_a[2], b0 = sc_b[0], b1 = sc_b[1], b2 = sc_b[2];
+    // ---- phase B (registers) ----
+    if (row >= 0) {
+      p0 = u0 + b0 * p0; p1 = u1 + b1 * p1; p2 = u2 + b2 * p2;
+      s0 = w0 + b0 * s0; s1 = w1 + b1 * s1; s2 = w2 + b2 * s2;
+      x0 += a0 * p0; x1 += a1 * p1; x2 += a2 * p2;
+      r0 -= a0 * s0; r1 -= a1 * s1; r2 -= a2 * s2;
+      double ux = di * r0, uy = di * r1, uz = di * r2;
+      if (mt >= 0) {
+        double4 rm = ldcg256(me.MR[old] + mt), sm = ldcg256(me.MS[old] + mt), wm = ldcg256(me.MW[par] + mt);
+        double4 rn = make_double4(0, 0, 0, 0), sn = rn, wn = rn;
+        if (mt2 >= 0) { rn = ldcg256(me.MR[old] + mt2); sn = ldcg256(me.MS[old] + mt2); wn = ldcg256(me.MW[par] + mt2); }
+        const double4 rt = tag4(r0, r1, r2, tcur), st = tag4(s0, s1, s2, tcur);
+        const PeerWindowLL mw = peer_window_ll_at(q.win[o1], q.npos);
+        st256(mw.MR[par] + row, rt);
+        st256(mw.MS[par] + row, st);
+        if (mt2 >= 0 && o2 != o1) {
+          const PeerWindowLL mw2 = peer_window_ll_at(q.win[o2], q.npos);
+          st256(mw2.MR[par] + row, rt);
+          st256(mw2.MS[par] + row, st);
+        }
+        if (!has_tag(rm, told)) rm = ld_tagged(me.MR[old] + mt, told);
+        if (!has_tag(sm, told)) sm = ld_tagged(me.MS[old] + mt, told);
+        if (!has_tag(wm, tcur)) wm = ld_tagged(me.MW[par] + mt, tcur);
+        const double sm0 = wm.x + b0 * sm.x, sm1 = wm.y + b1 * sm.y, sm2 = wm.z + b2 * sm.z;
+        ux += c2 * (rm.x - a0 * sm0); uy += c2 * (rm.y - a1 * sm1); uz += c2 * (rm.z - a2 * sm2);
+        if (mt2 >= 0) {
+          if (!has_tag(rn, told)) rn = ld_tagged(me.MR[old] + mt2, told);
+          if (!has_tag(sn, told)) sn = ld_tagged(me.MS[old] + mt2, told);
+          if (!has_tag(wn, tcur)) wn = ld_tagged(me.MW[par] + mt2, tcur);
+          const double t0 = wn.x + b0 * sn.x, t1 = wn.y + b1 * sn.y, t2 = wn.z + b2 * sn.z;
+          ux += c3 * (rn.x - a0 * t0); uy += c3 * (rn.y - a1 * t1); uz += c3 * (rn.z - a2 * t2);
+        }
+      }
+      const double4 un = tag4(ux, uy, uz, old);            // parity of the NEXT iteration
+      u0 = un.x; u1 = un.y; u2 = un.z;
+#pragma unroll
+      for (int g = 0; g < kPeerMax; ++g)
+        if (g < q.world) st256(reinterpret_cast<double4*>(q.win[g] + kPeerHdr) + pos, un);
+    }
+    if (q.flush == 1) { __syncwarp(); if (lane == 0) __threadfence_system(); }
+    else if (q.flush == 2) { __syncthreads(); if (threadIdx.x == 0) __threadfence_system(); }
+    ++it;
+    if (timer) { const long long c = clock64(); c_upd += c - c_mark; c_mark = c; }
+  }
+  if (row >= 0) {
+    const double4 x = make_double4(x0, x1, x2, 0.0);
+    for (int g = 0; g < q.world; ++g) st256(peer_window_ll_at(q.win[g], q.npos).X + row, x);
+  }
+  peer_barrier_ll(q, grid, ++epoch);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    p.ctl->epoch = epoch;
+    p.ctl->cg_iters = it;
+    for (int c = 0; c < 3; ++c) { p.ctl->bnorm2[c] = sc_bb[c]; p.ctl->rnorm2[c] = sc_rr[c]; }
+    p.ctl->done = 1;
+    unsigned long long ns_end;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_end));
+    p.ctl->cyc_spmv += c_spmv;
+    p.ctl->cyc_update += c_upd;
+    p.ctl->cyc_total += clock64() - c_begin;
+    p.ctl->ns_total += (long long)(ns_end - ns_begin);
+    p.ctl->pcg_spmv_phases += c_spmv > 0 ? it + 1 : 0;
+    if (q.debug && q.rank == 0)
+      printf("[k_pcg_peer_ll_reg] iters %d: cycles/iter SpMV %lld, local reduce %lld, dot exchange %lld, update %lld\n", it,
              d_mv / (it + 1), d_red / (it + 1), d_dot / (it + 1), c_upd / (it > 0 ? it : 1));
   }
 }

@@ -20,8 +20,11 @@ variant = int(os.environ.get("IRA_SPMV_VARIANT", "0"))
 mode = int(os.environ.get("IRA_SHARD_MODE", "1"))      # 1 = barrier-free exchange, 2 = two cross-GPU barriers per iteration
 s = ira.Solver(device=lr, world_size=world, rank=rank, shard_mode=mode, spmv_variant=variant)
 s.comm_init(broadcast_unique_id(dist, ira.Solver, rank, device="cuda"))
-for name, g in (("tiny n=3000", G.small_graph(n=3000, extra=30000, sigma_n=0.03, outlier_frac=0.1, seed=41)),
-                ("config 3", G.random_graph())):
+cases = [("tiny n=3000", G.small_graph(n=3000, extra=30000, sigma_n=0.03, outlier_frac=0.1, seed=41)),
+         ("config 3", G.random_graph())]
+if os.environ.get("IRA_PROBE_ONLY"):
+    cases = [c for c in cases if os.environ["IRA_PROBE_ONLY"] in c[0]]
+for name, g in cases:
     s.upload(g.QQ, g.I, g.Q0, g.f)
     for cost, its in ((O.GEMAN_MCCLURE, 6), (O.L1, 12)):
         s.irls_resident(cost, sigma, its, -1.0)
