@@ -173,10 +173,11 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, world):
-    tag = "configs[2]" if world == 1 else f"configs[2] recipe scaled x{world} (weak scaling; x8 = configs[3] scale)"
+def workload_config(args, scale, world=None):
+    world = scale if world is None else world
+    tag = "configs[2]" if scale == 1 else f"configs[2] recipe scaled x{scale} (weak scaling; x8 = configs[3] scale)"
     return {
-        "workload": f"{tag}: synthetic random SO(3) graph n={N_NODES * world} m={M_EDGES * world} (path + uniform pairs, "
+        "workload": f"{tag}: synthetic random SO(3) graph n={N_NODES * scale} m={M_EDGES * scale} (path + uniform pairs, "
                     f"sigma_n=0.05 rad, 10% outliers, seed 20190319), {IRLS_ITERS} IRLS iters per step, cost {args.cost}, "
                     "sigma 5 deg, f=1",
         "cost": args.cost, "irls_iters_per_step": IRLS_ITERS, "cg_rtol": 1e-10,
@@ -207,7 +208,8 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    g = make_graph(world)
+    gscale = args.graph_scale or world
+    g = make_graph(gscale)
     cost = COSTS[args.cost]
     m, n, f = g.m, g.n, g.f
     from irotavg_b200.sharding import broadcast_unique_id, edge_shard
@@ -288,7 +290,8 @@ def run_ours(args):
     wall_ms = (time.perf_counter() - t_wall0) * 1000.0
     clocks = sampler.stop() if rank == 0 else None
     dev_ms = max_over_ranks(dev_ms)
-    value = world * IRLS_ITERS * args.steps / (dev_ms / 1000.0)        # units of the 1M-edge graph (m = world x 1M)
+    world_units = gscale                                               # m = gscale x 1M edges
+    value = world_units * IRLS_ITERS * args.steps / (dev_ms / 1000.0)   # units of the 1M-edge graph
     Q_res, w_res = s.download()
 
     # ---- the callers' default cost and Huber on the same graph (1 warm-up + 2 timed steps each) ----
@@ -309,7 +312,7 @@ def run_ours(args):
             b.synchronize()
             ms += a.elapsed_time(b)
         ms = max_over_ranks(ms)
-        other[nm] = {"value": world * IRLS_ITERS * 2 / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms / 2,
+        other[nm] = {"value": world_units * IRLS_ITERS * 2 / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms / 2,
                      "cg_iters_per_step": int(sum(oi.cg_iters))}
 
     # ---- N > 1: the same 1M-edge graph on N GPUs (strong scaling), 1 warm-up + 2 timed steps ------------
@@ -373,7 +376,7 @@ def run_ours(args):
         e2e_ms += ms
     barrier()
     e2e_ms = max_over_ranks(e2e_ms)
-    e2e_value = world * IRLS_ITERS * e2e_steps / (e2e_ms / 1000.0)
+    e2e_value = world_units * IRLS_ITERS * e2e_steps / (e2e_ms / 1000.0)
     h2d = I_loc.nbytes + QQ_loc.nbytes + Q0f.nbytes
     d2h = Q0f.nbytes + 8 * m_loc
     same = bool(np.array_equal(np.ascontiguousarray(pQ), Q_res))
@@ -382,7 +385,7 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     roof = None
     prof_share = None
-    if world == 1:
+    if world == 1 and gscale == 1:
         # (1) the SpMV inside the timed solve: block 0's in-kernel clocks of the persistent PCG kernel
         info = infos[-1]
         ph = info.profile.get("pcg_phases")
@@ -428,7 +431,7 @@ def run_ours(args):
     # ---- parity against the oracle on the run itself (bounded: the first 2 iterations) ----------
     cpu = None
     rms = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and gscale == 1:
         from oracle import irls_oracle as O
         v, kind, cores, sample, extra = cpu_port_run(g, cost, args.ref_iters)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
@@ -440,7 +443,7 @@ def run_ours(args):
 
     # ---- configs[4] (incremental rotAvg stream), bounded sample: first 1500 frames of the 10k-frame stream -------
     stream = None
-    if rank == 0 and world == 1 and not args.no_stream:
+    if rank == 0 and world == 1 and gscale == 1 and not args.no_stream:
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_stream
@@ -454,7 +457,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, gscale, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "upload_ms": info_e.upload_ms, "download_ms": info_e.download_ms,
@@ -494,6 +497,9 @@ def main():
     ap.add_argument("--cost", default="L1", choices=sorted(COSTS))
     ap.add_argument("--nccl-allreduce", action="store_true",
                     help="N > 1: edge shards + NCCL all-reduce per PCG iteration instead of the peer-memory solve")
+    ap.add_argument("--graph-scale", type=int, default=0,
+                    help="graph = configs[2] recipe x this (default: the number of GPUs); e.g. --gpus 1 --graph-scale 8 "
+                         "runs the 8-GPU workload on one GPU for comparison")
     ap.add_argument("--no-stream", action="store_true", help="skip the bounded configs[4] rotAvg-stream sample")
     ap.add_argument("--ref-iters", type=int, default=10, help="IRLS iterations in the CPU port's bounded sample")
     args = ap.parse_args()
