@@ -31,7 +31,7 @@ namespace ira {
 namespace cg = cooperative_groups;
 
 constexpr int kMstEdgeChunk = 32;
-constexpr int kMstNodeChunk = 32;
+constexpr int kMstNodeChunk = 16;
 constexpr unsigned long long kMstInf = ~0ull;
 
 struct MstCtl {
@@ -77,34 +77,20 @@ k_mst_labels(const int2* __restrict__ I, int64_t m, unsigned long long* label, M
     if (gtid == 0) ctl->changed[(pass + 1) % 3] = 0;
     bool moved = false;
     for (int64_t c = gtid; c < nchunks; c += nthreads) {
-      const int64_t k0 = c * kMstEdgeChunk;
-      const int cnt = (int)min((int64_t)kMstEdgeChunk, m - k0);
-      // the chunk's edges and the labels of their endpoints are fetched up front (independent loads, in flight
-      // together); the sequential sweep below then only forwards what it changed itself
-      int2 e[kMstEdgeChunk];
-      unsigned long long lu[kMstEdgeChunk], lv[kMstEdgeChunk];
-#pragma unroll 8
-      for (int q = 0; q < kMstEdgeChunk; ++q) e[q] = q < cnt ? __ldg(I + k0 + q) : make_int2(0, 0);
-#pragma unroll 8
-      for (int q = 0; q < kMstEdgeChunk; ++q) { lu[q] = __ldcg(label + e[q].x); lv[q] = __ldcg(label + e[q].y); }
-      int pn1 = -1, pn2 = -1;                                   // endpoints of the previous edge and what this
-      unsigned long long pl1 = 0, pl2 = 0;                      // thread left in their labels: chains move on in registers
-      for (int q = 0; q < cnt; ++q) {
-        const int2 ed = e[q];
-        if (ed.x == ed.y) continue;
-        unsigned long long tu = lu[q], tv = lv[q];
-        if (ed.x == pn1) tu = min(tu, pl1); else if (ed.x == pn2) tu = min(tu, pl2);
-        if (ed.y == pn1) tv = min(tv, pl1); else if (ed.y == pn2) tv = min(tv, pl2);
-        const unsigned long long k1 = (unsigned long long)(k0 + q) + 1ull;
+      const int64_t k0 = c * kMstEdgeChunk, k1 = min(m, k0 + (int64_t)kMstEdgeChunk);
+      for (int64_t k = k0; k < k1; ++k) {
+        const int2 e = __ldg(I + k);
+        if (e.x == e.y) continue;
+        const unsigned long long tu = __ldcg(label + e.x);
+        unsigned long long tv = __ldcg(label + e.y);
         if (tu != kMstInf) {                                  // flags[e1] && !flags[e2]  (:934)
-          const unsigned long long cand = mst_next(tu, k1);
-          if (cand < tv) { atomicMin(label + ed.y, cand); tv = cand; moved = true; }
+          const unsigned long long cand = mst_next(tu, (unsigned long long)k + 1ull);
+          if (cand < tv) { atomicMin(label + e.y, cand); tv = cand; moved = true; }
         }
         if (tv != kMstInf) {                                  // !flags[e1] && flags[e2]  (:950)
-          const unsigned long long cand = mst_next(tv, k1);
-          if (cand < tu) { atomicMin(label + ed.x, cand); tu = cand; moved = true; }
+          const unsigned long long cand = mst_next(tv, (unsigned long long)k + 1ull);
+          if (cand < tu) { atomicMin(label + e.x, cand); moved = true; }
         }
-        pn1 = ed.x; pl1 = tu; pn2 = ed.y; pl2 = tv;
       }
     }
     if (__any_sync(0xffffffffu, moved) && (threadIdx.x & 31) == 0) atomicOr(&ctl->changed[slot], 1);
@@ -129,51 +115,25 @@ k_mst_propagate(const int2* __restrict__ I, const double* __restrict__ QQ, int64
     if (gtid == 0) ctl->changed[(pass + 1) % 3] = 0;
     bool waiting = false;
     for (int c = gtid; c < nchunks; c += nthreads) {
-      const int p0 = c * kMstNodeChunk;
-      const int cnt = min(kMstNodeChunk, n - p0);
-      // phase 1: everything that does not depend on other nodes' progress, for the whole chunk at once
-      int vv[kMstNodeChunk], uu[kMstNodeChunk];              // node, parent (-1: nothing to do)
-      double4 qq[kMstNodeChunk];
-#pragma unroll 4
-      for (int q = 0; q < kMstNodeChunk; ++q) {
-        vv[q] = q < cnt ? order[p0 + q] : -1;
-        uu[q] = -1;
-      }
-#pragma unroll 4
-      for (int q = 0; q < kMstNodeChunk; ++q) {
-        const int v = vv[q];
-        if (v < 0 || __ldcg(done + v)) { vv[q] = -1; continue; }
+      const int p0 = c * kMstNodeChunk, p1 = min(n, p0 + kMstNodeChunk);
+      for (int pos = p0; pos < p1; ++pos) {
+        const int v = order[pos];
+        if (__ldcg(done + v)) continue;
         const unsigned long long lab = label[v];
-        if (lab == kMstInf) { if (pass == 0) ++unreached; vv[q] = -1; continue; }
+        if (lab == kMstInf) { if (pass == 0) ++unreached; continue; }
         const int64_t k = (int64_t)(lab & 0xffffffffull) - 1;
         const int2 e = __ldg(I + k);
-        uu[q] = e.x == v ? e.y : e.x;
-        qq[q] = make_double4(QQ[k], QQ[ldqq + k], QQ[2 * ldqq + k], QQ[3 * ldqq + k]);
-        if (e.x == v) qq[q].w = -qq[q].w;                    // QQj_inv(3) *= -1  (:956-957)
-      }
-      // phase 2: in label order; a parent this thread has just finished is forwarded in registers, so a chain
-      // that is contiguous in label order advances a whole chunk per pass
-      int last = -1;
-      double4 lastQ = make_double4(0, 0, 0, 1);
-      unsigned int finished = 0u;
-      for (int q = 0; q < cnt; ++q) {
-        const int v = vv[q];
-        if (v < 0) continue;
-        const int u = uu[q];
-        double4 qu;
-        if (u == last) qu = lastQ;
-        else if (__ldcg(done + u)) { __threadfence(); qu = ldcg256(Q + u); }
-        else { waiting = true; continue; }
-        double4 qv;
-        if (v >= f_init) { qv = quat_mult(qq[q], qu); st256(Q + v, qv); }   // one product per node (:941 / :958)
-        else qv = ldcg256(Q + v);                            // known rotations are kept but still propagate (:939,953)
-        last = v; lastQ = qv;
-        finished |= 1u << q;
-      }
-      if (finished) {
-        __threadfence();                                     // the rotations are published before their flags
-        for (int q = 0; q < cnt; ++q)
-          if ((finished >> q) & 1u) atomicExch(done + vv[q], 1);
+        const int u = e.x == v ? e.y : e.x;
+        if (!__ldcg(done + u)) { waiting = true; continue; }
+        if (v >= f_init) {                                   // do not change known rotations (:939,953)
+          __threadfence();                                   // the parent's Q was published before its flag
+          const double4 qu = ldcg256(Q + u);
+          double4 qq = make_double4(QQ[k], QQ[ldqq + k], QQ[2 * ldqq + k], QQ[3 * ldqq + k]);
+          if (e.x == v) qq.w = -qq.w;                        // QQj_inv(3) *= -1  (:956-957)
+          st256(Q + v, quat_mult(qq, qu));
+          __threadfence();
+        }
+        atomicExch(done + v, 1);
       }
     }
     if (__any_sync(0xffffffffu, waiting) && (threadIdx.x & 31) == 0) atomicOr(&ctl->changed[slot], 1);
