@@ -271,6 +271,26 @@ def test_pair_preconditioner_l1_late_iterations(built_lib):
         assert O.geodesic_rms(Q1, Q0, g.f) <= RMS_TOL
 
 
+def test_three_by_three_blocks_vs_pairs_and_oracle(built_lib):
+    """Late L1 iterations: letting single nodes join a stiff pair (3x3 blocks, pair_theta3) must cut the PCG
+    iterations well below the pairs-only count, in every PCG variant, and the result must still be the exact
+    solve's (direct oracle, 20 iterations, the regime where the blocks matter)."""
+    import irotavg_b200 as ira
+    g = G.small_graph(n=4000, extra=40000, sigma_n=0.05, outlier_frac=0.1, sigma_init=0.1, seed=77)
+    ref = O.irls(g.QQ, g.I, None, O.L1, SIGMA, g.Q0, g.f, 20, -1.0, solver="direct")
+    with ira.Solver(pair_theta3=0.0) as s2:
+        Q2, w2, i2 = s2.irls(g.QQ, g.I, None, O.L1, SIGMA, g.Q0, g.f, 20, -1.0)
+    assert O.geodesic_rms(Q2, ref.Q, g.f) <= RMS_TOL
+    for kind in (0, 6, 1):
+        with ira.Solver(solver=kind) as s3:
+            Q3, w3, i3 = s3.irls(g.QQ, g.I, None, O.L1, SIGMA, g.Q0, g.f, 20, -1.0)
+        assert i3.cg_hit_max == 0
+        assert sum(i3.cg_iters[10:]) * 1.3 < sum(i2.cg_iters[10:]), (kind, i2.cg_iters, i3.cg_iters)
+        assert np.allclose(i3.scores, ref.scores, rtol=1e-6, atol=1e-12)
+        assert O.geodesic_rms(Q3, ref.Q, g.f) <= RMS_TOL
+        assert np.allclose(w3, ref.weights, rtol=1e-5, atol=1e-8)
+
+
 @pytest.mark.parametrize("lpr", [2, 4, 8, 16, 32])
 def test_lanes_per_row_variants(built_lib, lpr):
     import irotavg_b200 as ira
