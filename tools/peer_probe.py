@@ -22,6 +22,9 @@ s = ira.Solver(device=lr, world_size=world, rank=rank, shard_mode=mode, spmv_var
 s.comm_init(broadcast_unique_id(dist, ira.Solver, rank, device="cuda"))
 cases = [("tiny n=3000", G.small_graph(n=3000, extra=30000, sigma_n=0.03, outlier_frac=0.1, seed=41)),
          ("config 3", G.random_graph())]
+scale = int(os.environ.get("IRA_PROBE_SCALE", "0"))
+if scale > 1:                                        # the weak-scaling workload of bench.py --gpus <scale>
+    cases = [(f"config 3 x{scale}", G.random_graph(n=100_000 * scale, m=1_000_000 * scale))]
 if os.environ.get("IRA_PROBE_ONLY"):
     cases = [c for c in cases if os.environ["IRA_PROBE_ONLY"] in c[0]]
 for name, g in cases:
