@@ -467,6 +467,17 @@ ira_status solve_pcg_persistent(ira_context* h) {
   const int grid = std::max(1, std::min(h->nslices, h->sms * h->pcg_blocks_per_sm));
   ProfScope ps(h, KC_PCG);
   void* fn = nullptr;
+  if (h->nslices <= h->sms * kMwGroups && !(h->opt.solver & 4) && h->opt.spmv_variant == 0) {
+    // a few thousand nodes: several warps per slice (latency chain of the SpMV cut by kMwWarps), fewer blocks
+    PcgRegParams pr;
+    pr.base = pp;
+    pr.RS0r = h->R.as<double4>(); pr.RS0s = h->S.as<double4>(); pr.RS1r = h->R2.as<double4>(); pr.RS1s = h->S2.as<double4>();
+    void* rargs[] = {(void*)&pr};
+    const int g2 = std::max(1, cdiv(h->nslices, kMwGroups));
+    IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_pcg_persistent_reg_mw, dim3(g2), dim3(kPcgThreads), rargs, 0, h->stream));
+    h->launches++;
+    return IRA_OK;
+  }
   if (h->nslices <= grid * (kPcgThreads / 32) && !(h->opt.solver & 4)) {   // one row per lane: state in registers
     PcgRegParams pr;
     pr.base = pp;

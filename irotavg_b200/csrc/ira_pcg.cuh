@@ -809,4 +809,184 @@ k_pcg_persistent_reg(const PcgRegParams q) {
   }
 }
 
+// ---- small graphs: several warps per slice ---------------------------------------------------------------
+// With one slice per warp the SpMV of a PCG iteration is a latency chain - width / 4 batches of 4 gathers, one
+// after the other (6 batches at degree ~22: ~5 us) - however few slices there are, and a graph of a few thousand
+// nodes (config 2: 142 slices; the global rotAvg calls of config 5) leaves 95 % of the warps idle.  Here
+// kMwWarps warps share a slice: warp `sub` takes batches sub, sub + kMwWarps, ... of every row, the partial sums
+// meet in shared memory (added in warp order: deterministic) and warp 0 of the group - the only one that keeps
+// the row's x, r, p, s in registers - does everything else exactly as k_pcg_persistent_reg.  Fewer blocks also
+// make the two grid barriers cheaper.
+constexpr int kMwWarps = 8;
+constexpr int kMwGroups = kPcgThreads / 32 / kMwWarps;     // slices per block
+
+__global__ void __launch_bounds__(kPcgThreads, 1)
+k_pcg_persistent_reg_mw(const PcgRegParams q) {
+  const PcgParams& p = q.base;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double red[kPcgNV * 32];
+  __shared__ double tot[kPcgNV];
+  __shared__ double sc_bb[3], sc_go[3], sc_ao[3], sc_a[3], sc_b[3], sc_rr[3];
+  __shared__ int sc_stop;
+  __shared__ double part[kMwGroups][kMwWarps][3][32];
+  const int lane = threadIdx.x & 31;
+  const int group = (threadIdx.x >> 5) / kMwWarps, sub = (threadIdx.x >> 5) % kMwWarps;
+  const int slice = blockIdx.x * kMwGroups + group;                  // one slice per group of warps
+  const bool leader = sub == 0;
+  const bool has_pairs = p.npairs != nullptr && *p.npairs > 0;
+  int row = -1, width = 0, mt = -1, mt2 = -1;
+  int64_t base = 0;
+  if (slice < p.nslices) {
+    row = p.sell_row[slice * kSellC + lane];
+    width = p.slice_width[slice];
+    base = (int64_t)p.slice_off[slice] + lane;
+  }
+  double v[kPcgNV];
+#pragma unroll
+  for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
+  double x0 = 0, x1 = 0, x2 = 0, r0 = 0, r1 = 0, r2 = 0, p0 = 0, p1 = 0, p2 = 0, s0 = 0, s1 = 0, s2 = 0;
+  double u0 = 0, u1 = 0, u2 = 0, di = 0, c2 = 0, c3 = 0;
+  const int row_all = row;                                            // every warp of the group knows the row ...
+  if (!leader) row = -1;                                              // ... but only the leader owns its state
+  if (row >= 0) {
+    const double4 b = ldg256(p.B + row);
+    const double d = p.diag[row];
+    di = p.pc1 ? p.pc1[row] : (d > 0.0 ? 1.0 / d : 0.0);
+    r0 = b.x; r1 = b.y; r2 = b.z;
+    u0 = di * r0; u1 = di * r1; u2 = di * r2;
+    if (has_pairs) {
+      mt = p.mate[row];
+      if (mt >= 0) {
+        c2 = p.pc2[row];
+        const double4 bm = ldg256(p.B + mt);
+        u0 += c2 * bm.x; u1 += c2 * bm.y; u2 += c2 * bm.z;
+        mt2 = p.mate2[row];
+        if (mt2 >= 0) {
+          c3 = p.pc3[row];
+          const double4 b2 = ldg256(p.B + mt2);
+          u0 += c3 * b2.x; u1 += c3 * b2.y; u2 += c3 * b2.z;
+        }
+        st256(q.RS1r + row, b);                                      // "previous" buffer of iteration 0
+        st256(q.RS1s + row, make_double4(0, 0, 0, 0));
+      }
+    }
+    st256(p.U + row, make_double4(u0, u1, u2, 0.0));
+    v[0] = r0 * r0; v[1] = r1 * r1; v[2] = r2 * r2;
+  }
+  pcg_grid_reduce(v, p.partials, grid, red, tot);
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < 3; ++c) { sc_bb[c] = v[c]; sc_rr[c] = v[c]; sc_go[c] = 1.0; sc_ao[c] = 1.0; }
+    sc_stop = !(v[0] > 0.0 || v[1] > 0.0 || v[2] > 0.0);
+  }
+  __syncthreads();
+  int it = 0;
+  const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+  long long c_spmv = 0, c_upd = 0, c_mark = 0, c_begin = 0;
+  unsigned long long ns_begin = 0;
+  if (timer) { c_begin = c_mark = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_begin)); }
+
+  while (!sc_stop) {
+    double w0 = 0, w1 = 0, w2 = 0;
+    if (slice < p.nslices) {
+      // this warp's batches of the row; the row's own u was published by the leader before the last barrier
+      const double4 uo = row_all >= 0 ? ld256(p.U + row_all) : make_double4(0, 0, 0, 0);
+      double ax = 0, ay = 0, az = 0;
+      for (int j = sub * 4; j < width; j += 4 * kMwWarps) {
+        int c[4]; double ww[4]; double4 uc[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int64_t o = base + (int64_t)(j + t) * kSellC;
+          c[t] = __ldg(p.sell_col + o);
+          ww[t] = __ldg(p.sell_w2 + o);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) uc[t] = ld256(p.U + c[t]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { ax += ww[t] * (uo.x - uc[t].x); ay += ww[t] * (uo.y - uc[t].y); az += ww[t] * (uo.z - uc[t].z); }
+      }
+      part[group][sub][0][lane] = ax; part[group][sub][1][lane] = ay; part[group][sub][2][lane] = az;
+    }
+    __syncthreads();
+    if (leader && slice < p.nslices) {
+#pragma unroll
+      for (int t = 0; t < kMwWarps; ++t) { w0 += part[group][t][0][lane]; w1 += part[group][t][1][lane]; w2 += part[group][t][2][lane]; }
+    }
+    if (row >= 0) {
+      if (mt >= 0) st256(p.W + row, make_double4(w0, w1, w2, 0.0));   // the mate needs it after the barrier
+      v[0] = r0 * u0; v[1] = r1 * u1; v[2] = r2 * u2;
+      v[3] = u0 * w0; v[4] = u1 * w1; v[5] = u2 * w2;
+      v[6] = r0 * r0; v[7] = r1 * r1; v[8] = r2 * r2;
+    } else {
+#pragma unroll
+      for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
+    }
+    pcg_grid_reduce(v, p.partials, grid, red, tot);
+    if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; }
+    if (threadIdx.x == 0) {
+      bool conv = true;
+      for (int c = 0; c < 3; ++c) {
+        sc_rr[c] = v[6 + c];
+        if (!(v[6 + c] <= p.rtol2 * sc_bb[c])) conv = false;
+      }
+      if (conv || it >= p.max_iters) {
+        sc_stop = 1;
+      } else {
+        for (int c = 0; c < 3; ++c) {
+          const double gam = v[c], del = v[3 + c];
+          double beta = 0.0, den = del;
+          if (it > 0) {
+            beta = sc_go[c] > 0.0 ? gam / sc_go[c] : 0.0;
+            if (sc_ao[c] != 0.0) den = del - beta * gam / sc_ao[c];
+          }
+          const double alpha = den > 0.0 ? gam / den : 0.0;
+          sc_go[c] = gam; sc_ao[c] = alpha; sc_a[c] = alpha; sc_b[c] = beta;
+        }
+      }
+    }
+    __syncthreads();
+    if (sc_stop) break;
+    const double a0 = sc_a[0], a1 = sc_a[1], a2 = sc_a[2], b0 = sc_b[0], b1 = sc_b[1], b2 = sc_b[2];
+    if (row >= 0) {
+      p0 = u0 + b0 * p0; p1 = u1 + b1 * p1; p2 = u2 + b2 * p2;
+      s0 = w0 + b0 * s0; s1 = w1 + b1 * s1; s2 = w2 + b2 * s2;
+      x0 += a0 * p0; x1 += a1 * p1; x2 += a2 * p2;
+      r0 -= a0 * s0; r1 -= a1 * s1; r2 -= a2 * s2;
+      u0 = di * r0; u1 = di * r1; u2 = di * r2;
+      if (mt >= 0) {
+        double4* const curR = (it & 1) ? q.RS1r : q.RS0r;
+        double4* const curS = (it & 1) ? q.RS1s : q.RS0s;
+        const double4* const oldR = (it & 1) ? q.RS0r : q.RS1r;
+        const double4* const oldS = (it & 1) ? q.RS0s : q.RS1s;
+        const double4 rm = ld256(oldR + mt), sm = ld256(oldS + mt), wm = ld256(p.W + mt);
+        const double sm0 = wm.x + b0 * sm.x, sm1 = wm.y + b1 * sm.y, sm2 = wm.z + b2 * sm.z;   // the mate's new s
+        u0 += c2 * (rm.x - a0 * sm0); u1 += c2 * (rm.y - a1 * sm1); u2 += c2 * (rm.z - a2 * sm2);
+        if (mt2 >= 0) {
+          const double4 rn = ld256(oldR + mt2), sn = ld256(oldS + mt2), wn = ld256(p.W + mt2);
+          const double t0 = wn.x + b0 * sn.x, t1 = wn.y + b1 * sn.y, t2 = wn.z + b2 * sn.z;
+          u0 += c3 * (rn.x - a0 * t0); u1 += c3 * (rn.y - a1 * t1); u2 += c3 * (rn.z - a2 * t2);
+        }
+        st256(curR + row, make_double4(r0, r1, r2, 0.0));
+        st256(curS + row, make_double4(s0, s1, s2, 0.0));
+      }
+      st256(p.U + row, make_double4(u0, u1, u2, 0.0));
+    }
+    ++it;
+    grid.sync();
+    if (timer) { const long long c = clock64(); c_upd += c - c_mark; c_mark = c; }
+  }
+  if (row >= 0) st256(p.X + row, make_double4(x0, x1, x2, 0.0));
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    p.ctl->cg_iters = it;
+    for (int c = 0; c < 3; ++c) { p.ctl->bnorm2[c] = sc_bb[c]; p.ctl->rnorm2[c] = sc_rr[c]; }
+    p.ctl->done = 1;
+    unsigned long long ns_end;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_end));
+    p.ctl->cyc_spmv += c_spmv;
+    p.ctl->cyc_update += c_upd;
+    p.ctl->cyc_total += clock64() - c_begin;
+    p.ctl->ns_total += (long long)(ns_end - ns_begin);
+    p.ctl->pcg_spmv_phases += c_spmv > 0 ? it + 1 : 0;
+  }
+}
+
 }  // namespace ira
