@@ -455,6 +455,7 @@ ira_status solve_pcg_persistent(ira_context* h) {
   pp.mate2 = pairing ? h->mate2.as<int>() : nullptr;
   pp.pc3 = pairing ? h->pc3.as<double>() : nullptr;
   pp.n = h->n; pp.nslices = h->nslices; pp.max_iters = std::max(0, h->opt.cg_max_iters);
+  pp.debug = h->opt.profile == 2;
   pp.rtol2 = h->opt.cg_rtol * h->opt.cg_rtol;
   pp.sell_row = h->sell_row.as<int>(); pp.slice_off = h->slice_off.as<int>(); pp.slice_width = h->slice_width.as<int>();
   pp.sell_col = h->sell_col.as<int>(); pp.sell_w2 = h->sell_w2.as<double>();
@@ -509,12 +510,18 @@ ira_status solve_pcg_persistent(ira_context* h) {
 ira_status peer_setup(ira_context* h) {
   const int G = h->opt.world_size, n = std::max(h->n, 1);
   if (G > kPeerMax) { h->err = "peer-memory solve supports at most 8 ranks"; return IRA_ERR_INVALID_ARG; }
-  if (!h->comm) { h->err = "world_size > 1 but ira_comm_init was not called"; return IRA_ERR_COMM; }
+  if (G > 1 && !h->comm) { h->err = "world_size > 1 but ira_comm_init was not called"; return IRA_ERR_COMM; }
   void* before = h->peer_win.p;
   IRA_CUDA(h, h->peer_win.reserve(std::max(peer_window_bytes(n), peer_window_ll_bytes(std::max(h->npos, 1)))));
   IRA_CUDA(h, h->sell_colpos.reserve(sizeof(int) * (size_t)std::max<int64_t>(h->sell_total, 1)));
   // every rank takes the same decision: all see the same n, and a window only ever grows
-  if (h->peer_win.p != before || h->peer_exported != h->peer_win.p) {
+  if (G == 1) {                                            // the barrier-free kernel on one GPU: no mapping to exchange
+    if (h->peer_win.p != before || h->peer_exported != h->peer_win.p) {
+      IRA_CUDA(h, cudaMemsetAsync(h->peer_win.p, 0, h->peer_win.cap, h->stream));
+      h->peer_exported = h->peer_win.p;
+      h->peer_epoch = 0;
+    }
+  } else if (h->peer_win.p != before || h->peer_exported != h->peer_win.p) {
     for (int g = 0; g < kPeerMax; ++g)
       if (h->peer_mapped[g]) { cudaIpcCloseMemHandle(h->peer_mapped[g]); h->peer_mapped[g] = nullptr; }
     IRA_CUDA(h, cudaMemsetAsync(h->peer_win.p, 0, h->peer_win.cap, h->stream));
@@ -593,14 +600,14 @@ ira_status solve_pcg_peer(ira_context* h) {
   for (int g = 0; g < G; ++g) q.win[g] = (unsigned char*)(g == q.rank ? h->peer_win.p : h->peer_mapped[g]);
   q.epoch_base = h->peer_epoch;
   q.debug = (h->opt.spmv_variant & 7) == 7;
-  { const int fv = (h->opt.spmv_variant >> 3) & 3; q.flush = fv == 0 ? 1 : fv - 1; }   // default: one fence per warp
+  { const int fv = (h->opt.spmv_variant >> 3) & 3; q.flush = fv == 0 ? (G > 1 ? 1 : 0) : fv - 1; }   // default: one fence per warp
   q.sell_colpos = h->sell_colpos.as<int>();
   q.npos = h->npos;
   const int own = std::max(1, q.slice_hi - q.slice_lo);
   int grid = std::max(1, std::min(own, h->sms * h->peer_blocks_per_sm));
   ProfScope ps(h, KC_PCG);
   void* args[] = {(void*)&q};
-  const bool ll = h->opt.shard_mode == 1;                // 2 = the barrier version (A/B measurements)
+  const bool ll = h->opt.shard_mode == 1 || G == 1;      // 2 = the barrier version (A/B measurements)
   void* fn = ll ? (void*)k_pcg_peer_ll : (h->opt.spmv_variant == 1 ? (void*)k_pcg_peer<1, 4> : (void*)k_pcg_peer<0, 4>);
   int threads = kPeerThreads;
   // one row per lane fits (on EVERY rank: the largest slice range decides, so all ranks take the same kernel)
@@ -929,7 +936,8 @@ ira_status ira_problem_upload(ira_handle h, int64_t m, int64_t n_total, int32_t 
   }
   h->persistent = !h->fmt_csr && h->opt.world_size <= 1 && (h->opt.solver & 3) != 1 && h->pcg_blocks_per_sm > 0;
   h->peer = false;
-  if (h->opt.world_size > 1 && (h->opt.shard_mode == 1 || h->opt.shard_mode == 2)) {
+  if ((h->opt.world_size > 1 && (h->opt.shard_mode == 1 || h->opt.shard_mode == 2)) ||
+      (h->opt.world_size <= 1 && (h->opt.solver & 8))) {
     if (h->fmt_csr || h->pcg_blocks_per_sm <= 0) { h->err = "peer-memory solve needs the SELL pattern and cooperative launch"; return IRA_ERR_INVALID_ARG; }
     IRA_TRY(peer_setup(h));
     h->peer = true;

@@ -16,6 +16,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "ira_kernels.cuh"
 
@@ -449,6 +450,7 @@ struct PcgParams {
   double* dinv;
   const int* mate; const double* pc1; const double* pc2; const int* npairs;   // 2x2 / 3x3 block-Jacobi (null: Jacobi)
   const int* mate2; const double* pc3;                                         // third member of a 3x3 block, or -1
+  int debug;                                                                   // ira_options.profile == 2: print block 0's phase split
   double* partials;      // [gridDim.x][kPcgNV]
   Ctl* ctl;
 };
@@ -885,7 +887,9 @@ k_pcg_persistent_reg_mw(const PcgRegParams q) {
   unsigned long long ns_begin = 0;
   if (timer) { c_begin = c_mark = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_begin)); }
 
+  long long dbg[5] = {0, 0, 0, 0, 0}, dm = 0;
   while (!sc_stop) {
+    if (timer) dm = clock64();
     double w0 = 0, w1 = 0, w2 = 0;
     if (slice < p.nslices) {
       // this warp's batches of the row; the row's own u was published by the leader before the last barrier
@@ -907,6 +911,7 @@ k_pcg_persistent_reg_mw(const PcgRegParams q) {
       part[group][sub][0][lane] = ax; part[group][sub][1][lane] = ay; part[group][sub][2][lane] = az;
     }
     __syncthreads();
+    if (timer) { const long long c = clock64(); dbg[0] += c - dm; dm = c; }
     if (leader && slice < p.nslices) {
 #pragma unroll
       for (int t = 0; t < kMwWarps; ++t) { w0 += part[group][t][0][lane]; w1 += part[group][t][1][lane]; w2 += part[group][t][2][lane]; }
@@ -921,7 +926,7 @@ k_pcg_persistent_reg_mw(const PcgRegParams q) {
       for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
     }
     pcg_grid_reduce(v, p.partials, grid, red, tot);
-    if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; }
+    if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; dbg[1] += c - dm; dm = c; }
     if (threadIdx.x == 0) {
       bool conv = true;
       for (int c = 0; c < 3; ++c) {
@@ -944,6 +949,7 @@ k_pcg_persistent_reg_mw(const PcgRegParams q) {
       }
     }
     __syncthreads();
+    if (timer) { const long long c = clock64(); dbg[2] += c - dm; dm = c; }
     if (sc_stop) break;
     const double a0 = sc_a[0], a1 = sc_a[1], a2 = sc_a[2], b0 = sc_b[0], b1 = sc_b[1], b2 = sc_b[2];
     if (row >= 0) {
@@ -971,8 +977,9 @@ k_pcg_persistent_reg_mw(const PcgRegParams q) {
       st256(p.U + row, make_double4(u0, u1, u2, 0.0));
     }
     ++it;
+    if (timer) { const long long c = clock64(); dbg[3] += c - dm; dm = c; }
     grid.sync();
-    if (timer) { const long long c = clock64(); c_upd += c - c_mark; c_mark = c; }
+    if (timer) { const long long c = clock64(); c_upd += c - c_mark; c_mark = c; dbg[4] += c - dm; }
   }
   if (row >= 0) st256(p.X + row, make_double4(x0, x1, x2, 0.0));
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -986,6 +993,10 @@ k_pcg_persistent_reg_mw(const PcgRegParams q) {
     p.ctl->cyc_total += clock64() - c_begin;
     p.ctl->ns_total += (long long)(ns_end - ns_begin);
     p.ctl->pcg_spmv_phases += c_spmv > 0 ? it + 1 : 0;
+    if (p.debug)
+      printf("[k_pcg_persistent_reg_mw] %d blocks, iters %d: cycles/iter partial SpMV+sync %lld, reduce (grid barrier) %lld, "
+             "coefficients %lld, update %lld, grid barrier %lld\n", (int)gridDim.x, it, dbg[0] / (it + 1), dbg[1] / (it + 1),
+             dbg[2] / (it + 1), dbg[3] / (it > 0 ? it : 1), dbg[4] / (it > 0 ? it : 1));
   }
 }
 

@@ -379,10 +379,12 @@ __device__ __forceinline__ double4 ld_tagged(const double4* ptr, int p) {
   if (!has_tag(v, p)) {
     unsigned long long t0 = 0;
     unsigned int spins = 0;
+    unsigned int nap = 128;                                // back off: 100 000 polling threads would saturate L2
     do {
-      __nanosleep(20);
+      __nanosleep(nap);
+      if (nap < 2048) nap <<= 1;
       v = ldcg256(ptr);
-      if ((++spins & 0x3fffu) == 0u) {
+      if ((++spins & 0x3ffu) == 0u) {
         unsigned long long now;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
         if (t0 == 0) t0 = now;
@@ -727,6 +729,32 @@ k_pcg_peer_ll(const PcgPeerParams q) {
   }
 }
 
+// the same barrier with the window bases in shared memory (indexing the kernel-parameter array at run time would
+// copy the whole parameter block to every thread's stack)
+__device__ __forceinline__ void peer_barrier_ll_s(unsigned char* const* s_win, int rank, int world,
+                                                  cooperative_groups::grid_group& grid, unsigned long long epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) __threadfence_system();
+  grid.sync();
+  if (blockIdx.x == 0 && threadIdx.x < world)
+    st_relaxed_sys(reinterpret_cast<unsigned long long*>(s_win[threadIdx.x]) + rank, epoch);
+  if (threadIdx.x < world) {
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(s_win[rank]) + threadIdx.x;
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
+    while (ld_relaxed_sys_u64(f) < epoch) {
+      if ((++spins & 0xfffu) == 0u) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 20000000000ull) asm volatile("trap;");
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 // Register-resident form of the barrier-free kernel: when a rank's slices fit one per warp (rows per rank <=
 // grid x warps x 32), every lane owns ONE row for the whole solve and keeps x, r, p, s, u and its block
 // coefficients in registers, like k_pcg_persistent_reg.  The vector update then touches memory only to publish
@@ -739,12 +767,16 @@ k_pcg_peer_ll_reg(const PcgPeerParams q) {
   cgx::grid_group grid = cgx::this_grid();
   __shared__ double red[kPcgNV * 32];
   __shared__ double tot[kPcgNV];
+  __shared__ double totx[kPcgNV];                          // sums over the ranks (tot: this rank's totals)
   __shared__ double sc_bb[3], sc_go[3], sc_ao[3], sc_a[3], sc_b[3], sc_rr[3];
   __shared__ int sc_stop;
+  __shared__ unsigned char* s_win[kPeerMax];               // kernel-parameter arrays indexed at run time would be
+  if (threadIdx.x < kPeerMax) s_win[threadIdx.x] = q.win[threadIdx.x];   // copied to every thread's stack
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int gwarp = blockIdx.x + gridDim.x * (threadIdx.x >> 5);
   const int nwarps = gridDim.x * (blockDim.x >> 5);
-  const PeerWindowLL me = peer_window_ll_at(q.win[q.rank], q.npos);
+  const PeerWindowLL me = peer_window_ll_at(s_win[q.rank], q.npos);
   const bool has_pairs = p.npairs != nullptr && *p.npairs > 0;
   unsigned long long epoch = q.epoch_base;
   double v[kPcgNV];
@@ -788,7 +820,7 @@ k_pcg_peer_ll_reg(const PcgPeerParams q) {
     sc_stop = !(v[0] > 0.0 || v[1] > 0.0 || v[2] > 0.0);
   }
   __syncthreads();
-  peer_barrier_ll(q, grid, ++epoch);
+  peer_barrier_ll_s(s_win, q.rank, q.world, grid, ++epoch);
 
   // ---- this lane's row -------------------------------------------------------------------------------
   const int slice = q.slice_lo + gwarp;                    // <= 1 slice per warp (checked by the host)
@@ -822,7 +854,6 @@ k_pcg_peer_ll_reg(const PcgPeerParams q) {
   int it = 0;
   const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
   long long c_spmv = 0, c_upd = 0, c_mark = 0, c_begin = 0;
-  long long d_mv = 0, d_red = 0, d_dot = 0, d_t = 0;
   unsigned long long ns_begin = 0;
   if (timer) { c_begin = c_mark = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_begin)); }
 
@@ -836,8 +867,8 @@ k_pcg_peer_ll_reg(const PcgPeerParams q) {
     if (row >= 0) {
       if (mt >= 0) {
         const double4 wt = tag4(w0, w1, w2, tcur);
-        st256(peer_window_ll_at(q.win[o1], q.npos).MW[par] + row, wt);
-        if (mt2 >= 0 && o2 != o1) st256(peer_window_ll_at(q.win[o2], q.npos).MW[par] + row, wt);
+        st256(peer_window_ll_at(s_win[o1], q.npos).MW[par] + row, wt);
+        if (mt2 >= 0 && o2 != o1) st256(peer_window_ll_at(s_win[o2], q.npos).MW[par] + row, wt);
       }
       v[0] = r0 * u0; v[1] = r1 * u1; v[2] = r2 * u2;
       v[3] = u0 * w0; v[4] = u1 * w1; v[5] = u2 * w2;
@@ -846,23 +877,21 @@ k_pcg_peer_ll_reg(const PcgPeerParams q) {
 #pragma unroll
       for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
     }
-    if (timer) { d_t = clock64(); d_mv += d_t - c_mark; }
     pcg_grid_reduce(v, p.partials, grid, red, tot);
-    if (timer) { const long long c = clock64(); d_red += c - d_t; d_t = c; }
     ++epoch;
     if (blockIdx.x == 0 && threadIdx.x < q.world * kPcgNV) {
       const int g = threadIdx.x / kPcgNV, k = threadIdx.x % kPcgNV;
-      st_dot16(peer_window_ll_at(q.win[g], q.npos).dots + ((par * kPeerMax + q.rank) * 16 + k) * 2, v[k], epoch);
+      st_dot16(peer_window_ll_at(s_win[g], q.npos).dots + ((par * kPeerMax + q.rank) * 16 + k) * 2, tot[k], epoch);   // tot: the rank totals
     }
     if (threadIdx.x < kPcgNV) {
       double t = 0.0;
       for (int g = 0; g < q.world; ++g) t += ld_dot16(me.dots + ((par * kPeerMax + g) * 16 + threadIdx.x) * 2, epoch);
-      tot[threadIdx.x] = t;
+      totx[threadIdx.x] = t;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < kPcgNV; ++k) v[k] = tot[k];
-    if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; d_dot += c - d_t; }
+    for (int k = 0; k < kPcgNV; ++k) v[k] = totx[k];
+    if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; }
     if (threadIdx.x == 0) {
       bool conv = true;
       for (int c = 0; c < 3; ++c) {
@@ -895,36 +924,39 @@ k_pcg_peer_ll_reg(const PcgPeerParams q) {
       r0 -= a0 * s0; r1 -= a1 * s1; r2 -= a2 * s2;
       double ux = di * r0, uy = di * r1, uz = di * r2;
       if (mt >= 0) {
-        double4 rm = ldcg256(me.MR[old] + mt), sm = ldcg256(me.MS[old] + mt), wm = ldcg256(me.MW[par] + mt);
-        double4 rn = make_double4(0, 0, 0, 0), sn = rn, wn = rn;
-        if (mt2 >= 0) { rn = ldcg256(me.MR[old] + mt2); sn = ldcg256(me.MS[old] + mt2); wn = ldcg256(me.MW[par] + mt2); }
-        const double4 rt = tag4(r0, r1, r2, tcur), st = tag4(s0, s1, s2, tcur);
-        const PeerWindowLL mw = peer_window_ll_at(q.win[o1], q.npos);
-        st256(mw.MR[par] + row, rt);
-        st256(mw.MS[par] + row, st);
-        if (mt2 >= 0 && o2 != o1) {
-          const PeerWindowLL mw2 = peer_window_ll_at(q.win[o2], q.npos);
-          st256(mw2.MR[par] + row, rt);
-          st256(mw2.MS[par] + row, st);
+        {                                                  // publish my (r, s) first: the mates are waiting for them
+          const double4 rt = tag4(r0, r1, r2, tcur), st = tag4(s0, s1, s2, tcur);
+          const PeerWindowLL mw = peer_window_ll_at(s_win[o1], q.npos);
+          st256(mw.MR[par] + row, rt);
+          st256(mw.MS[par] + row, st);
+          if (mt2 >= 0 && o2 != o1) {
+            const PeerWindowLL mw2 = peer_window_ll_at(s_win[o2], q.npos);
+            st256(mw2.MR[par] + row, rt);
+            st256(mw2.MS[par] + row, st);
+          }
         }
-        if (!has_tag(rm, told)) rm = ld_tagged(me.MR[old] + mt, told);
-        if (!has_tag(sm, told)) sm = ld_tagged(me.MS[old] + mt, told);
-        if (!has_tag(wm, tcur)) wm = ld_tagged(me.MW[par] + mt, tcur);
-        const double sm0 = wm.x + b0 * sm.x, sm1 = wm.y + b1 * sm.y, sm2 = wm.z + b2 * sm.z;
-        ux += c2 * (rm.x - a0 * sm0); uy += c2 * (rm.y - a1 * sm1); uz += c2 * (rm.z - a2 * sm2);
+        {
+          double4 rm = ldcg256(me.MR[old] + mt), sm = ldcg256(me.MS[old] + mt), wm = ldcg256(me.MW[par] + mt);
+          if (!has_tag(rm, told)) rm = ld_tagged(me.MR[old] + mt, told);
+          if (!has_tag(sm, told)) sm = ld_tagged(me.MS[old] + mt, told);
+          if (!has_tag(wm, tcur)) wm = ld_tagged(me.MW[par] + mt, tcur);
+          ux += c2 * (rm.x - a0 * (wm.x + b0 * sm.x)); uy += c2 * (rm.y - a1 * (wm.y + b1 * sm.y));
+          uz += c2 * (rm.z - a2 * (wm.z + b2 * sm.z));
+        }
         if (mt2 >= 0) {
+          double4 rn = ldcg256(me.MR[old] + mt2), sn = ldcg256(me.MS[old] + mt2), wn = ldcg256(me.MW[par] + mt2);
           if (!has_tag(rn, told)) rn = ld_tagged(me.MR[old] + mt2, told);
           if (!has_tag(sn, told)) sn = ld_tagged(me.MS[old] + mt2, told);
           if (!has_tag(wn, tcur)) wn = ld_tagged(me.MW[par] + mt2, tcur);
-          const double t0 = wn.x + b0 * sn.x, t1 = wn.y + b1 * sn.y, t2 = wn.z + b2 * sn.z;
-          ux += c3 * (rn.x - a0 * t0); uy += c3 * (rn.y - a1 * t1); uz += c3 * (rn.z - a2 * t2);
+          ux += c3 * (rn.x - a0 * (wn.x + b0 * sn.x)); uy += c3 * (rn.y - a1 * (wn.y + b1 * sn.y));
+          uz += c3 * (rn.z - a2 * (wn.z + b2 * sn.z));
         }
       }
       const double4 un = tag4(ux, uy, uz, old);            // parity of the NEXT iteration
       u0 = un.x; u1 = un.y; u2 = un.z;
 #pragma unroll
       for (int g = 0; g < kPeerMax; ++g)
-        if (g < q.world) st256(reinterpret_cast<double4*>(q.win[g] + kPeerHdr) + pos, un);
+        if (g < q.world) st256(reinterpret_cast<double4*>(s_win[g] + kPeerHdr) + pos, un);
     }
     if (q.flush == 1) { __syncwarp(); if (lane == 0) __threadfence_system(); }
     else if (q.flush == 2) { __syncthreads(); if (threadIdx.x == 0) __threadfence_system(); }
@@ -933,9 +965,9 @@ k_pcg_peer_ll_reg(const PcgPeerParams q) {
   }
   if (row >= 0) {
     const double4 x = make_double4(x0, x1, x2, 0.0);
-    for (int g = 0; g < q.world; ++g) st256(peer_window_ll_at(q.win[g], q.npos).X + row, x);
+    for (int g = 0; g < q.world; ++g) st256(peer_window_ll_at(s_win[g], q.npos).X + row, x);
   }
-  peer_barrier_ll(q, grid, ++epoch);
+  peer_barrier_ll_s(s_win, q.rank, q.world, grid, ++epoch);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     p.ctl->epoch = epoch;
     p.ctl->cg_iters = it;
@@ -948,9 +980,6 @@ k_pcg_peer_ll_reg(const PcgPeerParams q) {
     p.ctl->cyc_total += clock64() - c_begin;
     p.ctl->ns_total += (long long)(ns_end - ns_begin);
     p.ctl->pcg_spmv_phases += c_spmv > 0 ? it + 1 : 0;
-    if (q.debug && q.rank == 0)
-      printf("[k_pcg_peer_ll_reg] iters %d: cycles/iter SpMV %lld, local reduce %lld, dot exchange %lld, update %lld\n", it,
-             d_mv / (it + 1), d_red / (it + 1), d_dot / (it + 1), c_upd / (it > 0 ? it : 1));
   }
 }
 

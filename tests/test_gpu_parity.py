@@ -232,11 +232,13 @@ def test_large_angle_identity_start(solver):
     assert O.geodesic_rms(Q, ref.Q, g.f) <= RMS_TOL
 
 
-@pytest.mark.parametrize("solver_kind", [1, 2, 6])
+@pytest.mark.parametrize("solver_kind", [1, 2, 6, 8, 12])
 @pytest.mark.parametrize("maker", ["random", "kitti", "tiny"])
 def test_solver_variants(built_lib, solver_kind, maker):
     """solver 1 = one kernel per CG step (SELL SpMV, host-polled), 2 = persistent cooperative PCG
-    (register-resident state when one row per lane fits), 6 = persistent with HBM-resident vectors."""
+    (register-resident state when one row per lane fits), 6 = persistent with HBM-resident vectors, 8 / 12 = the
+    barrier-free kernels of the multi-GPU path (self-validating data, ira_peer.cuh) on ONE GPU, register- /
+    HBM-resident."""
     import irotavg_b200 as ira
     if maker == "random":
         g = G.small_graph(n=3000, extra=30000, sigma_n=0.03, outlier_frac=0.1, seed=31, f=2, fixed_anywhere=True)
@@ -262,7 +264,7 @@ def test_pair_preconditioner_l1_late_iterations(built_lib):
     g = G.random_graph(n=10000, m=100000)
     with ira.Solver(pair_theta=0.0) as s0:
         Q0, w0, i0 = s0.irls(g.QQ, g.I, None, O.L1, SIGMA, g.Q0, g.f, 16, -1.0)
-    for kind in (0, 6, 1):                    # persistent (registers / HBM state), one-kernel-per-step
+    for kind in (0, 6, 1, 8, 12):             # persistent (registers / HBM state), one-kernel-per-step, barrier-free
         with ira.Solver(solver=kind) as s1:
             Q1, w1, i1 = s1.irls(g.QQ, g.I, None, O.L1, SIGMA, g.Q0, g.f, 16, -1.0)
         assert i0.cg_hit_max == 0 and i1.cg_hit_max == 0
@@ -281,7 +283,7 @@ def test_three_by_three_blocks_vs_pairs_and_oracle(built_lib):
     with ira.Solver(pair_theta3=0.0) as s2:
         Q2, w2, i2 = s2.irls(g.QQ, g.I, None, O.L1, SIGMA, g.Q0, g.f, 20, -1.0)
     assert O.geodesic_rms(Q2, ref.Q, g.f) <= RMS_TOL
-    for kind in (0, 6, 1):
+    for kind in (0, 6, 1, 8, 12):
         with ira.Solver(solver=kind) as s3:
             Q3, w3, i3 = s3.irls(g.QQ, g.I, None, O.L1, SIGMA, g.Q0, g.f, 20, -1.0)
         assert i3.cg_hit_max == 0

@@ -30,10 +30,11 @@ ap.add_argument("--solver", type=int, default=0)
 ap.add_argument("--check-every", type=int, default=None)
 ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--time-kernels", action="store_true")
+ap.add_argument("--debug-phases", action="store_true", help="ira_options.profile = 2: the small-graph PCG kernel prints its phase split")
 a = ap.parse_args()
 
 g = G.kitti_like_graph() if a.kitti else G.random_graph(n=a.n, m=a.m)
-s = ira.Solver(profile=not a.no_profile, lanes_per_row=a.lpr, solver=a.solver, cg_check_every=a.check_every,
+s = ira.Solver(profile=2 if a.debug_phases else (not a.no_profile), lanes_per_row=a.lpr, solver=a.solver, cg_check_every=a.check_every,
                spmv_variant=a.variant)
 s.upload(g.QQ, g.I, g.Q0, g.f)
 for _ in range(a.reps):
