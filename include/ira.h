@@ -65,11 +65,14 @@ typedef struct ira_options {
                               with that many lanes per row (forces solver 1)                       */
   int32_t world_size;      /* >1: edges are sharded over ranks, node vectors all-reduced (NCCL)   */
   int32_t rank;
-  int32_t profile;         /* 1: record CUDA-event timings per kernel class into ira_stats        */
+  int32_t profile;         /* 1: record CUDA-event timings per kernel class into ira_stats; 2: also let the
+                              small-graph PCG kernel print its per-iteration phase split (debugging)          */
   int32_t solver;          /* PCG driver: 0 = auto (persistent cooperative kernel on one GPU), 1 = one
                               kernel per CG step with host-polled convergence, 2 = persistent;
                               +4 = persistent kernel keeps its vectors in HBM even when one row per
-                              lane would let them live in registers (A/B measurement)               */
+                              lane would let them live in registers (A/B measurement);
+                              +8 = one GPU only: the barrier-free kernel of the multi-GPU path
+                              (self-validating data instead of grid barriers; measured slower, kept for A/B) */
   int32_t spmv_variant;    /* experiment knob: gather flavour / unroll of the SELL SpMV (0 = default)  */
   int32_t small_path;      /* window-sized problems (n_total <= 64, 1 <= n_free <= 32, m <= 256) in
                               ira_l1ra_irls run as ONE single-block kernel with dense Cholesky solves

@@ -45,6 +45,33 @@ def test_host_mirror_compiles_and_takes_the_early_returns(tmp_path, built_lib):
     assert calls[2, 2:4].tolist() == [2, 1]
 
 
+def test_rmat2quat_branches_match_oracle(tmp_path, built_lib):
+    """CPU: the host mirror's rmat2quat takes the reference's four branches (trace > 0 and the three largest-diagonal
+    cases, src/ViewGraph.cpp:1175-1203) exactly like the oracle, and quat2rmat_rowmajor inverts it."""
+    exe = str(tmp_path / "rmat_main")
+    libdir = os.path.dirname(built_lib)
+    subprocess.run(["g++", "-std=c++11", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), "-I",
+                    os.path.join(ROOT, "irotavg_b200", "host"), "-I", os.path.join(ROOT, "tests", "cpp"),
+                    os.path.join(ROOT, "tests", "cpp", "rmat_main.cpp"), "-o", exe, "-L", libdir, "-lira",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    rng = np.random.default_rng(3)
+    qs = rng.standard_normal((200, 4))
+    qs /= np.linalg.norm(qs, axis=1, keepdims=True)
+    # rotations by ~pi about x, y, z and tilted axes: trace <= 0, every largest-diagonal branch
+    for ax in np.vstack([np.eye(3), [[1, 1, 0.2], [0.1, 1, 1], [1, 0.3, 1]]]):
+        for ang in (np.pi, np.pi - 1e-3, 3.0):
+            a = ax / np.linalg.norm(ax)
+            qs = np.vstack([qs, np.r_[a * np.sin(ang / 2), np.cos(ang / 2)]])
+    Rs = np.array([O.quat2rmat(q) for q in qs])
+    inp = "\n".join(" ".join(f"{v:.17g}" for v in R.ravel()) for R in Rs) + "\n"
+    out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout
+    got = np.array(out.split(), dtype=np.float64).reshape(len(Rs), 13)
+    ref = np.array([O.rmat2quat(R) for R in Rs])
+    assert (np.trace(Rs, axis1=1, axis2=2) <= 0).sum() >= 10
+    assert np.max(np.abs(got[:, :4] - ref)) <= 1e-15
+    assert np.max(np.abs(got[:, 4:].reshape(-1, 3, 3) - Rs)) <= 1e-14
+
+
 def test_oracle_rotavg_recovers_a_noise_free_stream():
     """Pins the oracle's rotAvg restatement independently of any implementation: exact measurements, views start
     at identity (src/Pose.hpp:43), view 0 is the gauge -> every window solve lands on the ground truth."""
