@@ -34,8 +34,11 @@ constexpr int kPeerThreads = 512;      // 16 warps: 128 registers per thread (76
 struct PeerWindow {
   double4* U;        // [n]  full search-direction input vector u = M^-1 r (every owner writes its rows)
   double4* X;        // [n]  solution, all-gathered at the end of the solve
-  double4* MR[2];    // [n]  ping-pong (r, s) of paired rows, written by the row's owner into the MATE's owner
-  double4* MS[2];
+  double4* MR0;      // [2][n] ping-pong (r, s) of paired rows, written by the row's owner into the MATE's owner
+  double4* MS0;      //        (buffer b = pointer + b * n: no arrays in the struct, see PeerWindowLL)
+  size_t stride;
+  __host__ __device__ double4* MR(int b) const { return MR0 + (size_t)b * stride; }
+  __host__ __device__ double4* MS(int b) const { return MS0 + (size_t)b * stride; }
   double4* MW;       // [n]  w = A u of paired rows, same routing
   double* dots;      // [2][kPeerMax][16]
   unsigned long long* flags;   // [kPeerMax]
@@ -47,8 +50,8 @@ __host__ __device__ inline size_t peer_window_bytes(int n) { return kPeerHdr + (
 __host__ __device__ inline PeerWindow peer_window_at(unsigned char* base, int n) {
   PeerWindow w;
   double4* v = reinterpret_cast<double4*>(base + kPeerHdr);
-  w.U = v; w.X = v + (size_t)n; w.MR[0] = v + (size_t)2 * n; w.MR[1] = v + (size_t)3 * n;
-  w.MS[0] = v + (size_t)4 * n; w.MS[1] = v + (size_t)5 * n; w.MW = v + (size_t)6 * n;
+  w.U = v; w.X = v + (size_t)n; w.MR0 = v + (size_t)2 * n; w.MS0 = v + (size_t)4 * n; w.MW = v + (size_t)6 * n;
+  w.stride = (size_t)n;
   w.flags = reinterpret_cast<unsigned long long*>(base);
   w.dots = reinterpret_cast<double*>(base + 256);
   return w;
@@ -170,8 +173,8 @@ k_pcg_peer(const PcgPeerParams q) {
             const double c3 = p.pc3[row];
             u0.x += c3 * b2.x; u0.y += c3 * b2.y; u0.z += c3 * b2.z;
           }
-          st256(me.MR[1] + row, b);
-          st256(me.MS[1] + row, make_double4(0, 0, 0, 0));
+          st256(me.MR(1) + row, b);
+          st256(me.MS(1) + row, make_double4(0, 0, 0, 0));
         }
       }
       st256(me.U + row, u0);
@@ -289,25 +292,25 @@ k_pcg_peer(const PcgPeerParams q) {
           if (mt >= 0) {
             // the mate's new residual from its previous (r, s) and this iteration's w - all delivered before
             // the dot-product barrier
-            const double4 rm = ld256(me.MR[old] + mt), sm = ld256(me.MS[old] + mt), wm = ld256(me.MW + mt);
+            const double4 rm = ld256(me.MR(old) + mt), sm = ld256(me.MS(old) + mt), wm = ld256(me.MW + mt);
             const double c2 = p.pc2[row];
             const double sm0 = wm.x + b0 * sm.x, sm1 = wm.y + b1 * sm.y, sm2 = wm.z + b2 * sm.z;
             un.x += c2 * (rm.x - a0 * sm0); un.y += c2 * (rm.y - a1 * sm1); un.z += c2 * (rm.z - a2 * sm2);
             const int o1 = peer_owner(q, mt);
             const PeerWindow mw = peer_window_at(q.win[o1], p.n);
-            st256(mw.MR[cur] + row, r);
-            st256(mw.MS[cur] + row, ss);
+            st256(mw.MR(cur) + row, r);
+            st256(mw.MS(cur) + row, ss);
             const int m2 = p.mate2[row];
             if (m2 >= 0) {
-              const double4 rn = ld256(me.MR[old] + m2), sn = ld256(me.MS[old] + m2), wn = ld256(me.MW + m2);
+              const double4 rn = ld256(me.MR(old) + m2), sn = ld256(me.MS(old) + m2), wn = ld256(me.MW + m2);
               const double c3 = p.pc3[row];
               const double t0 = wn.x + b0 * sn.x, t1 = wn.y + b1 * sn.y, t2 = wn.z + b2 * sn.z;
               un.x += c3 * (rn.x - a0 * t0); un.y += c3 * (rn.y - a1 * t1); un.z += c3 * (rn.z - a2 * t2);
               const int o2 = peer_owner(q, m2);
               if (o2 != o1) {
                 const PeerWindow mw2 = peer_window_at(q.win[o2], p.n);
-                st256(mw2.MR[cur] + row, r);
-                st256(mw2.MS[cur] + row, ss);
+                st256(mw2.MR(cur) + row, r);
+                st256(mw2.MS(cur) + row, ss);
               }
             }
           }
@@ -452,19 +455,22 @@ __device__ __forceinline__ void sell_row_apply_tagged(const int* __restrict__ se
 
 // Window layout of the LL variant: U | X | MR[2] | MS[2] | MW[2] (9 n double4), dots [2][kPeerMax][16] as
 // {value, epoch} pairs (2 doubles each -> [2][kPeerMax][32]), flags.
-struct PeerWindowLL {
-  double4 *U, *X, *MR[2], *MS[2], *MW[2];
+struct PeerWindowLL {          // no arrays inside: indexing a local struct at run time would put it on the stack
+  double4 *U, *X, *MR0, *MS0, *MW0;   // buffer b of MR / MS / MW = pointer + b * stride
+  size_t stride;
   double* dots;
   unsigned long long* flags;
+  __host__ __device__ double4* MR(int b) const { return MR0 + (size_t)b * stride; }
+  __host__ __device__ double4* MS(int b) const { return MS0 + (size_t)b * stride; }
+  __host__ __device__ double4* MW(int b) const { return MW0 + (size_t)b * stride; }
 };
 __host__ __device__ inline size_t peer_window_ll_bytes(int npos) { return kPeerHdr + (size_t)9 * npos * sizeof(double4); }
 __host__ __device__ inline PeerWindowLL peer_window_ll_at(unsigned char* base, int n) {
   PeerWindowLL w;
   double4* v = reinterpret_cast<double4*>(base + kPeerHdr);
   w.U = v; w.X = v + (size_t)n;
-  w.MR[0] = v + (size_t)2 * n; w.MR[1] = v + (size_t)3 * n;
-  w.MS[0] = v + (size_t)4 * n; w.MS[1] = v + (size_t)5 * n;
-  w.MW[0] = v + (size_t)6 * n; w.MW[1] = v + (size_t)7 * n;
+  w.MR0 = v + (size_t)2 * n; w.MS0 = v + (size_t)4 * n; w.MW0 = v + (size_t)6 * n;
+  w.stride = (size_t)n;
   w.flags = reinterpret_cast<unsigned long long*>(base);
   w.dots = reinterpret_cast<double*>(base + 256);
   return w;
@@ -539,10 +545,10 @@ k_pcg_peer_ll(const PcgPeerParams q) {
           // buffer 1 with tag 1; every other buffer gets the tag its first writer will NOT use, so that stale
           // rows of an earlier solve can never be mistaken for fresh ones
           const double4 inval = tag4(0.0, 0.0, 0.0, 1);
-          st256(me.MR[1] + row, tag4(b.x, b.y, b.z, 1));
-          st256(me.MS[1] + row, inval);
-          st256(me.MR[0] + row, inval); st256(me.MS[0] + row, inval);
-          st256(me.MW[0] + row, inval); st256(me.MW[1] + row, inval);
+          st256(me.MR(1) + row, tag4(b.x, b.y, b.z, 1));
+          st256(me.MS(1) + row, inval);
+          st256(me.MR(0) + row, inval); st256(me.MS(0) + row, inval);
+          st256(me.MW(0) + row, inval); st256(me.MW(1) + row, inval);
         }
       }
       st256(me.U + (s * kSellC + lane), tag4(u0.x, u0.y, u0.z, 0));   // u lives in SELL-position order: a warp's 32 rows are 1 KB contiguous
@@ -588,9 +594,9 @@ k_pcg_peer_ll(const PcgPeerParams q) {
           if (mt >= 0) {                                                   // my block mates need a copy of my w
             const double4 wt = tag4(ax, ay, az, tcur);
             const int o1 = peer_owner(q, mt);
-            st256(peer_window_ll_at(q.win[o1], q.npos).MW[par] + row, wt);
+            st256(peer_window_ll_at(q.win[o1], q.npos).MW(par) + row, wt);
             const int m2 = p.mate2[row];
-            if (m2 >= 0) { const int o2 = peer_owner(q, m2); if (o2 != o1) st256(peer_window_ll_at(q.win[o2], q.npos).MW[par] + row, wt); }
+            if (m2 >= 0) { const int o2 = peer_owner(q, m2); if (o2 != o1) st256(peer_window_ll_at(q.win[o2], q.npos).MW(par) + row, wt); }
           }
         }
         const double4 r = ld256(p.R + row);
@@ -662,32 +668,32 @@ k_pcg_peer_ll(const PcgPeerParams q) {
             // a mate's new residual from its previous (r, s) (parity `old`) and this iteration's w (parity `par`)
             // issue every load first, validate afterwards: one L2 round trip instead of up to six in a row
             const int m2 = p.mate2[row];
-            double4 rm = ldcg256(me.MR[old] + mt), sm = ldcg256(me.MS[old] + mt), wm = ldcg256(me.MW[par] + mt);
+            double4 rm = ldcg256(me.MR(old) + mt), sm = ldcg256(me.MS(old) + mt), wm = ldcg256(me.MW(par) + mt);
             double4 rn = make_double4(0, 0, 0, 0), sn = rn, wn = rn;
-            if (m2 >= 0) { rn = ldcg256(me.MR[old] + m2); sn = ldcg256(me.MS[old] + m2); wn = ldcg256(me.MW[par] + m2); }
-            if (!has_tag(rm, told)) rm = ld_tagged(me.MR[old] + mt, told);
-            if (!has_tag(sm, told)) sm = ld_tagged(me.MS[old] + mt, told);
-            if (!has_tag(wm, tcur)) wm = ld_tagged(me.MW[par] + mt, tcur);
+            if (m2 >= 0) { rn = ldcg256(me.MR(old) + m2); sn = ldcg256(me.MS(old) + m2); wn = ldcg256(me.MW(par) + m2); }
+            if (!has_tag(rm, told)) rm = ld_tagged(me.MR(old) + mt, told);
+            if (!has_tag(sm, told)) sm = ld_tagged(me.MS(old) + mt, told);
+            if (!has_tag(wm, tcur)) wm = ld_tagged(me.MW(par) + mt, tcur);
             const double c2 = p.pc2[row];
             const double sm0 = wm.x + b0 * sm.x, sm1 = wm.y + b1 * sm.y, sm2 = wm.z + b2 * sm.z;
             ux += c2 * (rm.x - a0 * sm0); uy += c2 * (rm.y - a1 * sm1); uz += c2 * (rm.z - a2 * sm2);
             const double4 rt = tag4(r.x, r.y, r.z, tcur), st = tag4(ss.x, ss.y, ss.z, tcur);
             const int o1 = peer_owner(q, mt);
             const PeerWindowLL mw = peer_window_ll_at(q.win[o1], q.npos);
-            st256(mw.MR[par] + row, rt);
-            st256(mw.MS[par] + row, st);
+            st256(mw.MR(par) + row, rt);
+            st256(mw.MS(par) + row, st);
             if (m2 >= 0) {
-              if (!has_tag(rn, told)) rn = ld_tagged(me.MR[old] + m2, told);
-              if (!has_tag(sn, told)) sn = ld_tagged(me.MS[old] + m2, told);
-              if (!has_tag(wn, tcur)) wn = ld_tagged(me.MW[par] + m2, tcur);
+              if (!has_tag(rn, told)) rn = ld_tagged(me.MR(old) + m2, told);
+              if (!has_tag(sn, told)) sn = ld_tagged(me.MS(old) + m2, told);
+              if (!has_tag(wn, tcur)) wn = ld_tagged(me.MW(par) + m2, tcur);
               const double c3 = p.pc3[row];
               const double t0 = wn.x + b0 * sn.x, t1 = wn.y + b1 * sn.y, t2 = wn.z + b2 * sn.z;
               ux += c3 * (rn.x - a0 * t0); uy += c3 * (rn.y - a1 * t1); uz += c3 * (rn.z - a2 * t2);
               const int o2 = peer_owner(q, m2);
               if (o2 != o1) {
                 const PeerWindowLL mw2 = peer_window_ll_at(q.win[o2], q.npos);
-                st256(mw2.MR[par] + row, rt);
-                st256(mw2.MS[par] + row, st);
+                st256(mw2.MR(par) + row, rt);
+                st256(mw2.MS(par) + row, st);
               }
             }
           }
@@ -771,7 +777,10 @@ k_pcg_peer_ll_reg(const PcgPeerParams q) {
   __shared__ double sc_bb[3], sc_go[3], sc_ao[3], sc_a[3], sc_b[3], sc_rr[3];
   __shared__ int sc_stop;
   __shared__ unsigned char* s_win[kPeerMax];               // kernel-parameter arrays indexed at run time would be
-  if (threadIdx.x < kPeerMax) s_win[threadIdx.x] = q.win[threadIdx.x];   // copied to every thread's stack
+  if (threadIdx.x == 0) {                                  // copied to every thread's stack
+#pragma unroll
+    for (int g = 0; g < kPeerMax; ++g) s_win[g] = q.win[g];
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int gwarp = blockIdx.x + gridDim.x * (threadIdx.x >> 5);
@@ -804,10 +813,10 @@ k_pcg_peer_ll_reg(const PcgPeerParams q) {
             u0.x += c3 * b2.x; u0.y += c3 * b2.y; u0.z += c3 * b2.z;
           }
           const double4 inval = tag4(0.0, 0.0, 0.0, 1);
-          st256(me.MR[1] + row, tag4(b.x, b.y, b.z, 1));
-          st256(me.MS[1] + row, inval);
-          st256(me.MR[0] + row, inval); st256(me.MS[0] + row, inval);
-          st256(me.MW[0] + row, inval); st256(me.MW[1] + row, inval);
+          st256(me.MR(1) + row, tag4(b.x, b.y, b.z, 1));
+          st256(me.MS(1) + row, inval);
+          st256(me.MR(0) + row, inval); st256(me.MS(0) + row, inval);
+          st256(me.MW(0) + row, inval); st256(me.MW(1) + row, inval);
         }
       }
       st256(me.U + (s * kSellC + lane), tag4(u0.x, u0.y, u0.z, 0));
@@ -852,10 +861,10 @@ k_pcg_peer_ll_reg(const PcgPeerParams q) {
     }
   }
   int it = 0;
-  const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
-  long long c_spmv = 0, c_upd = 0, c_mark = 0, c_begin = 0;
+  // only the wall time of the solve is kept (block 0): phase clocks would cost every thread ~10 registers, and
+  // this kernel is already 600 B of stack over budget at 85 registers per thread
   unsigned long long ns_begin = 0;
-  if (timer) { c_begin = c_mark = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_begin)); }
+  if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_begin));
 
   while (!sc_stop) {
     const int par = it & 1, old = par ^ 1;
@@ -867,8 +876,8 @@ k_pcg_peer_ll_reg(const PcgPeerParams q) {
     if (row >= 0) {
       if (mt >= 0) {
         const double4 wt = tag4(w0, w1, w2, tcur);
-        st256(peer_window_ll_at(s_win[o1], q.npos).MW[par] + row, wt);
-        if (mt2 >= 0 && o2 != o1) st256(peer_window_ll_at(s_win[o2], q.npos).MW[par] + row, wt);
+        st256(peer_window_ll_at(s_win[o1], q.npos).MW(par) + row, wt);
+        if (mt2 >= 0 && o2 != o1) st256(peer_window_ll_at(s_win[o2], q.npos).MW(par) + row, wt);
       }
       v[0] = r0 * u0; v[1] = r1 * u1; v[2] = r2 * u2;
       v[3] = u0 * w0; v[4] = u1 * w1; v[5] = u2 * w2;
@@ -891,7 +900,6 @@ k_pcg_peer_ll_reg(const PcgPeerParams q) {
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kPcgNV; ++k) v[k] = totx[k];
-    if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; }
     if (threadIdx.x == 0) {
       bool conv = true;
       for (int c = 0; c < 3; ++c) {
@@ -927,27 +935,27 @@ k_pcg_peer_ll_reg(const PcgPeerParams q) {
         {                                                  // publish my (r, s) first: the mates are waiting for them
           const double4 rt = tag4(r0, r1, r2, tcur), st = tag4(s0, s1, s2, tcur);
           const PeerWindowLL mw = peer_window_ll_at(s_win[o1], q.npos);
-          st256(mw.MR[par] + row, rt);
-          st256(mw.MS[par] + row, st);
+          st256(mw.MR(par) + row, rt);
+          st256(mw.MS(par) + row, st);
           if (mt2 >= 0 && o2 != o1) {
             const PeerWindowLL mw2 = peer_window_ll_at(s_win[o2], q.npos);
-            st256(mw2.MR[par] + row, rt);
-            st256(mw2.MS[par] + row, st);
+            st256(mw2.MR(par) + row, rt);
+            st256(mw2.MS(par) + row, st);
           }
         }
         {
-          double4 rm = ldcg256(me.MR[old] + mt), sm = ldcg256(me.MS[old] + mt), wm = ldcg256(me.MW[par] + mt);
-          if (!has_tag(rm, told)) rm = ld_tagged(me.MR[old] + mt, told);
-          if (!has_tag(sm, told)) sm = ld_tagged(me.MS[old] + mt, told);
-          if (!has_tag(wm, tcur)) wm = ld_tagged(me.MW[par] + mt, tcur);
+          double4 rm = ldcg256(me.MR(old) + mt), sm = ldcg256(me.MS(old) + mt), wm = ldcg256(me.MW(par) + mt);
+          if (!has_tag(rm, told)) rm = ld_tagged(me.MR(old) + mt, told);
+          if (!has_tag(sm, told)) sm = ld_tagged(me.MS(old) + mt, told);
+          if (!has_tag(wm, tcur)) wm = ld_tagged(me.MW(par) + mt, tcur);
           ux += c2 * (rm.x - a0 * (wm.x + b0 * sm.x)); uy += c2 * (rm.y - a1 * (wm.y + b1 * sm.y));
           uz += c2 * (rm.z - a2 * (wm.z + b2 * sm.z));
         }
         if (mt2 >= 0) {
-          double4 rn = ldcg256(me.MR[old] + mt2), sn = ldcg256(me.MS[old] + mt2), wn = ldcg256(me.MW[par] + mt2);
-          if (!has_tag(rn, told)) rn = ld_tagged(me.MR[old] + mt2, told);
-          if (!has_tag(sn, told)) sn = ld_tagged(me.MS[old] + mt2, told);
-          if (!has_tag(wn, tcur)) wn = ld_tagged(me.MW[par] + mt2, tcur);
+          double4 rn = ldcg256(me.MR(old) + mt2), sn = ldcg256(me.MS(old) + mt2), wn = ldcg256(me.MW(par) + mt2);
+          if (!has_tag(rn, told)) rn = ld_tagged(me.MR(old) + mt2, told);
+          if (!has_tag(sn, told)) sn = ld_tagged(me.MS(old) + mt2, told);
+          if (!has_tag(wn, tcur)) wn = ld_tagged(me.MW(par) + mt2, tcur);
           ux += c3 * (rn.x - a0 * (wn.x + b0 * sn.x)); uy += c3 * (rn.y - a1 * (wn.y + b1 * sn.y));
           uz += c3 * (rn.z - a2 * (wn.z + b2 * sn.z));
         }
@@ -961,7 +969,6 @@ k_pcg_peer_ll_reg(const PcgPeerParams q) {
     if (q.flush == 1) { __syncwarp(); if (lane == 0) __threadfence_system(); }
     else if (q.flush == 2) { __syncthreads(); if (threadIdx.x == 0) __threadfence_system(); }
     ++it;
-    if (timer) { const long long c = clock64(); c_upd += c - c_mark; c_mark = c; }
   }
   if (row >= 0) {
     const double4 x = make_double4(x0, x1, x2, 0.0);
@@ -975,11 +982,9 @@ k_pcg_peer_ll_reg(const PcgPeerParams q) {
     p.ctl->done = 1;
     unsigned long long ns_end;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_end));
-    p.ctl->cyc_spmv += c_spmv;
-    p.ctl->cyc_update += c_upd;
-    p.ctl->cyc_total += clock64() - c_begin;
+    p.ctl->cyc_total += (long long)(ns_end - ns_begin);     // 1 "cycle" = 1 ns here: the host only needs the ratio
     p.ctl->ns_total += (long long)(ns_end - ns_begin);
-    p.ctl->pcg_spmv_phases += c_spmv > 0 ? it + 1 : 0;
+    p.ctl->pcg_spmv_phases += it + 1;
   }
 }
 
