@@ -13,9 +13,13 @@
 //       (an all-gather by direct P2P stores, fused into the update loop - the transfer of row i overlaps the
 //       arithmetic of row i+1), and, for rows of 2x2 preconditioner blocks whose mate lives on another rank,
 //       its (r, s) and w to the mate's owner only.
-// Cross-GPU barrier = local grid barrier, then block 0 stores an epoch number into every peer's flag array
-// (after a system-scope fence), then every block polls its own rank's flags: 2 per PCG iteration.
-// Chronopoulos-Gear recurrences as in k_pcg_persistent (same arithmetic per row).
+// Three kernels, selected by ira_options.shard_mode (all parity-tested, bitwise identical across ranks):
+//   k_pcg_peer          (shard_mode 2)  two cross-GPU barriers per PCG iteration: block barrier + one system-scope
+//                                       fence per block + grid barrier + an epoch number stored into every peer's
+//                                       flag array + every block polls its own rank's flags;
+//   k_pcg_peer_ll       (shard_mode 1)  no barrier, no flag: every exchanged datum validates itself (below);
+//   k_pcg_peer_ll_reg   (shard_mode 1, rows per rank <= 148 x 24 x 32)  the same with x, r, p, s, u in registers.
+// Chronopoulos-Gear recurrences and the 2x2 / 3x3 block-Jacobi arithmetic as in k_pcg_persistent (ira_pcg.cuh).
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -75,11 +79,6 @@ struct PcgPeerParams {
 
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
 }
 __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
   unsigned long long v;
@@ -361,7 +360,8 @@ k_pcg_peer(const PcgPeerParams q) {
 //     simply re-reads (L2-coherent load) until the row has arrived - from another SM or another GPU alike,
 //     which also removes the LOCAL grid barrier after the vector update;
 //   * dot products: {value, epoch} in one 16-byte store (single-copy atomic), polled per value;
-//   * (r, s, w) copies for 2x2 / 3x3 blocks: parity-tagged like u, in buffers indexed by that parity.
+//   * (r, s, w) copies for 2x2 / 3x3 blocks: tagged like u, in buffers indexed by the iteration parity k & 1 and
+//     carrying tag (k >> 1) & 1, so that consecutive uses of one buffer carry different tags.
 // What is left per iteration: ONE local grid barrier (inside the block-ordered dot-product reduction) and one
 // NVLink store->poll flight.  Write-after-read safety comes from the dot products themselves: a rank sends its
 // partial sums only after all its blocks finished the SpMV (reading u), and nobody can produce the next u
