@@ -149,7 +149,9 @@ def run_reference_arm(args):
     scale = max(1, args.gpus)                      # the same workload as our arm at N GPUs (weak scaling: graph x N)
     g = make_graph(scale)
     cost = COSTS[args.cost]
-    sample_iters = max(3, args.ref_iters // scale)
+    # bounded sample: the first 10 IRLS iterations up to 2M edges, fewer on the larger graphs (a CPU step must stay
+    # under a minute): 10, 10, 5, 4 iterations at x1, x2, x4, x8
+    sample_iters = max(4, min(args.ref_iters, (2 * args.ref_iters) // scale))
     for _ in range(min(args.warmup, 1)):
         cpu_port_run(g, cost, 1)
     vals = []
@@ -478,6 +480,10 @@ def run_ours(args):
             line["other_costs"] = other
         if strong is not None:
             line["strong_scaling_1M_edges"] = strong
+        if gscale > 1:
+            line["value_note"] = (f"weak scaling: the graph is the configs[2] recipe x{gscale} ({m} edges); value = IRLS "
+                                  f"iterations/s x {gscale}, i.e. in units of the 1M-edge graph; plain IRLS iterations/s on "
+                                  f"this graph = value / {gscale}")
         if world > 1:
             ph = info.profile.get("pcg_phases") or {}
             line["pcg_us_per_iteration"] = 1e3 * ph.get("kernel_ms", 0.0) / max(1, int(sum(info.cg_iters)))
