@@ -34,7 +34,7 @@ def build_cli(force: bool = False) -> str:
     """The `l1_irls` executable (host/l1_irls_cli.cpp: the reference's ral/test.cpp flow over the adapter
     header), linked against libira.so with an rpath relative to the executable."""
     src = os.path.join(HOST, "l1_irls_cli.cpp")
-    deps = [src, os.path.join(HOST, "l1_irls.hpp"), os.path.join(INCLUDE, "ira.h")]
+    deps = [src, os.path.join(HOST, "l1_irls.hpp"), os.path.join(HOST, "ral_text_io.hpp"), os.path.join(INCLUDE, "ira.h")]
     if (not force and os.path.exists(CLI)
             and all(os.path.getmtime(CLI) >= os.path.getmtime(d) for d in deps + [LIB])):
         return CLI

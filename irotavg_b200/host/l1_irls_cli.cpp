@@ -23,6 +23,7 @@
 #include <string>
 
 #include "l1_irls.hpp"
+#include "ral_text_io.hpp"
 
 namespace {
 
@@ -42,33 +43,6 @@ irotavg::Cost cost_from_name(const char* name) {          // names of ral/test.c
     if (s == names[c]) return (irotavg::Cost)c;
   die(std::string("Unknown string. ") + (name ? name : ""));
   return irotavg::Geman_McClure;
-}
-
-// Eigen's operator<< with IOFormat(precision): entries at `precision` significant digits, padded on the
-// left to the width of the widest entry, columns separated by one space, rows by '\n'.
-std::string eigen_style(const double* colmajor, long rows, long cols, long ld, const int* col_order, int precision) {
-  std::vector<std::string> cell((size_t)rows * cols);
-  size_t width = 0;
-  for (long i = 0; i < rows; ++i)
-    for (long j = 0; j < cols; ++j) {
-      std::ostringstream o;
-      o.precision(precision);
-      o << colmajor[(size_t)(col_order ? col_order[j] : j) * ld + i];
-      cell[(size_t)i * cols + j] = o.str();
-      width = std::max(width, o.str().size());
-    }
-  std::string out;
-  out.reserve((width + 1) * cell.size() + 1);
-  for (long i = 0; i < rows; ++i) {
-    if (i) out += '\n';
-    for (long j = 0; j < cols; ++j) {
-      if (j) out += ' ';
-      const std::string& c = cell[(size_t)i * cols + j];
-      out.append(width - c.size(), ' ');
-      out += c;
-    }
-  }
-  return out;
 }
 
 }  // namespace
@@ -171,7 +145,7 @@ int main(int argc, const char* argv[]) {
   int precision = 15;                                              // Eigen::FullPrecision for double
   if (const char* p = std::getenv("IRA_CLI_PRECISION")) precision = std::max(1, std::atoi(p));
   const int wxyz[4] = {3, 0, 1, 2};
-  out << eigen_style(Q.data(), n, 4, n, wxyz, precision) << "\n";
-  out << eigen_style(weights.data(), m, 1, m, nullptr, precision) << "\n";
+  out << ira_b200::eigen_style(Q.data(), n, 4, n, wxyz, precision) << "\n";
+  out << ira_b200::eigen_style(weights.data(), m, 1, m, nullptr, precision) << "\n";
   return 0;
 }

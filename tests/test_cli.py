@@ -36,6 +36,25 @@ def test_usage_and_bad_input_exit_codes(cli, tmp_path):
     assert r.returncode == 255                                          # both exits come before any device call
 
 
+def test_eigen_style_layout(tmp_path):
+    """CPU: the output layout is Eigen's `operator<<` with IOFormat(FullPrecision) - %.15g entries, every entry
+    right-aligned to the widest one of the whole matrix, one space between columns (ral/test.cpp:321-325)."""
+    exe = str(tmp_path / "textio_main")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["g++", "-std=c++11", "-O1", "-Wall", "-I", os.path.join(root, "irotavg_b200", "host"),
+                    os.path.join(root, "tests", "cpp", "textio_main.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    blocks = out.rstrip("\n").split("\n--\n")
+    vals = [[1.0, 12345.678901234567], [-0.5, 2e-9], [1.0 / 3.0, -7.0]]
+    cells = [[f"{v:.15g}" for v in row] for row in vals]
+    width = max(len(c) for row in cells for c in row)
+    assert blocks[0] == "\n".join(" ".join(c.rjust(width) for c in row) for row in cells)
+    assert blocks[1] == "\n".join(" ".join(c.rjust(width) for c in row[::-1]) for row in cells)     # column order argument
+    col = [f"{row[0]:.17g}" for row in vals]
+    w17 = max(len(c) for c in col)
+    assert blocks[2] == "\n".join(c.rjust(w17) for c in col)
+
+
 def _parse_output(path, n, m):
     lines = open(path).read().split("\n")
     assert lines[-1] == "" and len(lines) == n + m + 1
