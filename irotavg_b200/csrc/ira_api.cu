@@ -158,6 +158,19 @@ namespace {
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Two CUDA events that are destroyed on every return path (the IRA_TRY / IRA_CUDA macros return early on errors).
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaError_t create() {
+    cudaError_t e = cudaEventCreate(&a);
+    return e != cudaSuccess ? e : cudaEventCreate(&b);
+  }
+  ~EventPair() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+};
+
 cudaEvent_t prof_event(ira_context* h) {
   if (h->ev_used == h->ev_pool.size()) {
     cudaEvent_t e;
@@ -963,9 +976,9 @@ ira_status ira_irls_resident(ira_handle h, int32_t cost, double sigma, int32_t m
     memset(stats, 0, sizeof *stats);
     stats->t_upload_ms = up;
   }
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  IRA_CUDA(h, cudaEventCreate(&ev0));
-  IRA_CUDA(h, cudaEventCreate(&ev1));
+  EventPair evp;
+  IRA_CUDA(h, evp.create());
+  cudaEvent_t ev0 = evp.a, ev1 = evp.b;
   IRA_CUDA(h, cudaEventRecord(ev0, h->stream));
 
   const int n = h->n;
@@ -1033,8 +1046,6 @@ ira_status ira_irls_resident(ira_handle h, int32_t cost, double sigma, int32_t m
   IRA_CUDA(h, cudaStreamSynchronize(h->stream));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ev0, ev1);
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
   prof_collect(h, stats);
   if (iters_out) *iters_out = iters;
   if (runtime_s_out) *runtime_s_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -1481,9 +1492,9 @@ ira_status ira_init_mst_resident(ira_handle h, int32_t f_init, ira_mst_stats* st
   IRA_CUDA(h, h->mst_order2.reserve(sizeof(int) * (size_t)n));
   IRA_CUDA(h, h->mst_done.reserve(sizeof(int) * (size_t)n));
   IRA_CUDA(h, h->mst_ctl.reserve(sizeof(MstCtl)));
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  IRA_CUDA(h, cudaEventCreate(&ev0));
-  IRA_CUDA(h, cudaEventCreate(&ev1));
+  EventPair evp;
+  IRA_CUDA(h, evp.create());
+  cudaEvent_t ev0 = evp.a, ev1 = evp.b;
   IRA_CUDA(h, cudaEventRecord(ev0, h->stream));
   k_mst_init<<<cdiv(n, 256), 256, 0, h->stream>>>(h->mst_label.as<unsigned long long>(), h->mst_done.as<int>(),
                                                  h->mst_order.as<int>(), n, h->mst_ctl.as<MstCtl>());
@@ -1537,8 +1548,6 @@ ira_status ira_init_mst_resident(ira_handle h, int32_t f_init, ira_mst_stats* st
   IRA_CUDA(h, cudaStreamSynchronize(h->stream));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ev0, ev1);
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
   if (stats) {
     stats->passes_label = host.passes_label; stats->passes_propagate = host.passes_prop;
     stats->unreached = host.unreached; stats->t_ms = ms;
