@@ -32,14 +32,18 @@ def test_header_symbols_are_exported(built_lib):
 def test_struct_layout_matches_ctypes(tmp_path, built_lib):
     from irotavg_b200 import _lib
     prog = tmp_path / "sz.c"
-    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ira.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ira.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                     "sizeof(ira_options), sizeof(ira_stats), offsetof(ira_options, cg_rtol),"
-                    "offsetof(ira_stats, score), offsetof(ira_stats, n_residual));return 0;}\n")
+                    "offsetof(ira_stats, score), offsetof(ira_stats, n_residual), sizeof(ira_mst_stats),"
+                    "offsetof(ira_mst_stats, t_ms), offsetof(ira_options, shard_mode), offsetof(ira_options, pair_theta3));"
+                    "return 0;}\n")
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert [int(v) for v in out] == [C.sizeof(_lib.Options), C.sizeof(_lib.Stats), _lib.Options.cg_rtol.offset,
-                                     _lib.Stats.score.offset, _lib.Stats.n_residual.offset]
+                                     _lib.Stats.score.offset, _lib.Stats.n_residual.offset, C.sizeof(_lib.MstStats),
+                                     _lib.MstStats.t_ms.offset, _lib.Options.shard_mode.offset,
+                                     _lib.Options.pair_theta3.offset]
 
 
 def test_header_is_plain_c(tmp_path):
