@@ -1,6 +1,6 @@
 """Builds the C restatement (oracle/irls_oracle.c) into oracle/_build/libirls_oracle.so with gcc.
-Test / bench infrastructure only (see oracle/irls_oracle.py).  The reference itself cannot be
-compiled here (no Eigen / SuiteSparse), so there is no oracle/_ref."""
+Test / bench infrastructure only (see oracle/irls_oracle.py).  The reference itself is built by
+oracle/build_ref.py into oracle/_ref (small graphs only: its sparse solvers are dense stand-ins)."""
 import os
 import subprocess
 

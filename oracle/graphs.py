@@ -160,6 +160,29 @@ def small_graph(n=200, extra=1500, sigma_n=0.0, outlier_frac=0.0, sigma_init=0.2
     return Graph(I=I, QQ=QQ, Q0=Q0, Qgt=Qgt, f=f, name=name or f"small_n{n}")
 
 
+def banded_graph(n=400, band=6, loops=120, sigma_n=0.005, outlier_frac=0.05, sigma_init=0.1, seed=5, f=1,
+                 name=None) -> Graph:
+    """A small view-graph-like case for the dense reference build (oracle/_ref): smooth trajectory, band edges
+    (k-d, k) d = 1..band ordered by (j, i) like a SLAM run, plus `loops` random loop closures (5 % outliers)."""
+    rng = np.random.default_rng(seed)
+    Qgt = np.empty((n, 4))
+    Qgt[0] = _rand_quat(rng, 1)[0]
+    steps = _exp_quat(rng.standard_normal((n - 1, 3)) * 0.02)
+    for k in range(1, n):
+        Qgt[k] = quat_mult(Qgt[k - 1], steps[k - 1])
+    Qgt /= np.linalg.norm(Qgt, axis=1, keepdims=True)
+    bandI = np.concatenate([np.stack([np.arange(0, n - d), np.arange(d, n)], axis=1) for d in range(1, band + 1)])
+    bandI = bandI[np.lexsort((bandI[:, 0], bandI[:, 1]))]
+    lp = _distinct_pairs(rng, n, loops)
+    lp = lp[(lp[:, 1] - lp[:, 0]) > band]
+    I = np.concatenate([bandI, lp]).astype(np.int32)
+    out = np.zeros(I.shape[0], dtype=bool)
+    out[bandI.shape[0]:] = rng.random(lp.shape[0]) < outlier_frac
+    QQ = _measure(rng, Qgt, I, sigma_n, out)
+    Q0 = _init(rng, Qgt, f, sigma_init)
+    return Graph(I=I, QQ=QQ, Q0=Q0, Qgt=Qgt, f=f, name=name or f"banded_n{n}")
+
+
 # --------------------------------------------------------------------------------------------
 # RAL text format
 # --------------------------------------------------------------------------------------------

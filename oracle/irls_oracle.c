@@ -2,8 +2,8 @@
  *
  * TEST AND BENCH INFRASTRUCTURE ONLY: nothing under irotavg_b200/ or include/ links or calls this
  * file; tests/ use it as an independent checker of oracle/irls_oracle.py and bench.py times it as
- * the `cpu_baseline` / `--impl reference` arm.  PARITY UNPINNED (see oracle/irls_oracle.py): the
- * reference ships no expected outputs and cannot be built in this image.
+ * the `cpu_baseline` / `--impl reference` arm.  Pinned through oracle/irls_oracle.py, which tests/test_ref_pin.py
+ * holds to the reference's own ral/l1_irls.cpp compiled by oracle/build_ref.py (tests/test_c_oracle.py: C == numpy).
  *
  * Follows ral/l1_irls.cpp (paths relative to the reference tree):
  *   quat_mult :99-105   delta_rel :109-127   log_map :498-532   exp_map :471-492

@@ -4,10 +4,18 @@ TEST INFRASTRUCTURE ONLY.  Nothing in the product path (irotavg_b200/, include/)
 call, link or execute this file; only tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs use it, and only as the checker / reported baseline.
 
-PARITY UNPINNED: the reference ships no expected output, known-answer test or golden vector for
-this path (ral/test.cpp is a CLI, ral/data/ravg_input.txt is input only), and the reference
-cannot be compiled in this image (Eigen, SuiteSparseQR, UMFPACK absent, no network).  The pins
-this oracle is held to instead are (tests/test_oracle.py):
+PARITY PIN: the reference ships no expected output, known-answer test or golden vector for this path
+(ral/test.cpp is a CLI, ral/data/ravg_input.txt is input only), and its dependencies (Eigen, SuiteSparseQR,
+UMFPACK) are absent from this image.  Since round 2 the oracle is nevertheless pinned to the reference's OWN
+CODE: oracle/build_ref.py compiles ral/l1_irls.cpp and ral/test.cpp unmodified from /root/reference against
+stand-in headers for the three absent libraries (oracle/ref_shim/: eager-evaluation Eigen subset, dense
+Householder-QR SuiteSparseQR, dense partial-pivoting-LU UMFPACK) into oracle/_ref/, and
+tests/golden/make_golden_ref.py commits what that build produces (the CLI on the bundled fixture for four
+costs; all 14 costs, make_A, residuals, exp_map, init_mst, l1ra, l1ra->irls flows on seeded graphs).
+tests/test_ref_pin.py holds this oracle to those numbers (<= 1e-12 rad RMS) and, where oracle/_ref is present,
+to the live reference on fresh random graphs.  What stays unpinned is the arithmetic INSIDE the three third-party
+libraries (SPQR's / UMFPACK's elimination order, Eigen's vectorised reductions): rounding-level effects.
+Further pins (tests/test_oracle.py):
   1. noise-free known-answer graphs (ground truth recovered to ~1e-15 rad),
   2. agreement of three independent formulations of the linear step
      (dense QR least squares on D*A  ==  sparse LU on A^T D^2 A  ==  Jacobi-PCG),
