@@ -446,6 +446,15 @@ def run_ours(args):
         s2.close()
         rms = O.geodesic_rms(Q2, ref.Q, f)
 
+    # ---- parity of the timed run itself: all 30 iterations against the committed golden of the C restatement ----
+    rms30 = dev30 = None
+    gpath = os.path.join(ROOT, "tests", "golden", "cfg3_l1_30iters.npz")
+    if rank == 0 and world == 1 and gscale == 1 and args.cost == "L1" and os.path.exists(gpath):
+        from oracle import irls_oracle as O
+        gold = np.load(gpath)
+        rms30 = O.geodesic_rms(Q_res, gold["Q"], f)
+        dev30 = float(np.abs(np.array(infos[-1].scores) / gold["scores"] - 1).max())
+
     # ---- configs[4] (incremental rotAvg stream), bounded sample: first 1500 frames of the 10k-frame stream -------
     stream = None
     if rank == 0 and world == 1 and gscale == 1 and not args.no_stream:
@@ -472,6 +481,7 @@ def run_ours(args):
             "cg_iters_per_step": int(sum(info.cg_iters)), "cg_hit_max": int(info.cg_hit_max),
             "final_score": info.scores[-1] if info.scores else None,
             "geodesic_rms_vs_oracle_2iters_rad": rms,
+            "geodesic_rms_vs_oracle_30iters_rad": rms30, "max_score_rel_dev_vs_oracle_30iters": dev30,
         }
         if roof is not None:
             line["roofline"] = roof
