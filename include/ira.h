@@ -72,7 +72,8 @@ typedef struct ira_options {
                               +4 = persistent kernel keeps its vectors in HBM even when one row per
                               lane would let them live in registers (A/B measurement);
                               +8 = one GPU only: the barrier-free kernel of the multi-GPU path
-                              (self-validating data instead of grid barriers; measured slower, kept for A/B) */
+                              (self-validating data instead of grid barriers; measured slower, kept for A/B);
+                              +16 = do not use the matrix-in-shared-memory kernel (ira_pcg2.cuh; A/B)          */
   int32_t spmv_variant;    /* experiment knob: gather flavour / unroll of the SELL SpMV (0 = default)  */
   int32_t small_path;      /* window-sized problems (n_total <= 64, 1 <= n_free <= 32, m <= 256) in
                               ira_l1ra_irls run as ONE single-block kernel with dense Cholesky solves

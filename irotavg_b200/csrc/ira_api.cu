@@ -22,6 +22,7 @@
 
 #include "ira_kernels.cuh"
 #include "ira_pcg.cuh"
+#include "ira_pcg2.cuh"
 #include "ira_l1ra.cuh"
 #include "ira_mst.cuh"
 #include "ira_small.cuh"
@@ -110,6 +111,10 @@ struct ira_context {
   bool persistent = true;    // one cooperative kernel per linear solve
   bool pairing = false;      // 2x2 block-Jacobi active in the multi-kernel path
   int pcg_blocks_per_sm = 0;
+  // matrix-in-shared-memory PCG (ira_pcg2.cuh): cached entry columns per slice, entries per block, usable flag
+  std::vector<int> h_slice_width;
+  int pcg2_wcap = 0, pcg2_entries = 0;
+  bool pcg2_ok = false;
   DevBuf ctl, partials, bad, flush;
   Ctl* h_ctl = nullptr;  // pinned
 
@@ -492,6 +497,18 @@ ira_status solve_pcg_persistent(ira_context* h) {
     h->launches++;
     return IRA_OK;
   }
+  if (h->pcg2_ok && !(h->opt.solver & (4 | 16)) && h->opt.spmv_variant == 0) {
+    // one row per lane, state in registers, the matrix in shared memory (ira_pcg2.cuh)
+    Pcg2Params p2;
+    p2.reg.base = pp;
+    p2.reg.RS0r = h->R.as<double4>(); p2.reg.RS0s = h->S.as<double4>(); p2.reg.RS1r = h->R2.as<double4>(); p2.reg.RS1s = h->S2.as<double4>();
+    p2.wcap = h->pcg2_wcap; p2.smem_entries = h->pcg2_entries;
+    void* rargs[] = {(void*)&p2};
+    IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_pcg_smem, dim3(std::min(h->nslices, h->sms)), dim3(kPcg2Threads), rargs,
+                                            (size_t)h->pcg2_entries * 12 + 24 * kPcg2Threads, h->stream));
+    h->launches++;
+    return IRA_OK;
+  }
   if (h->nslices <= grid * (kPcgThreads / 32) && !(h->opt.solver & 4)) {   // one row per lane: state in registers
     PcgRegParams pr;
     pr.base = pp;
@@ -786,6 +803,48 @@ ira_status build_sell(ira_context* h) {
   return launch_check(h, "k_sell_inverse");
 }
 
+// Plan of the matrix-in-shared-memory PCG kernel (ira_pcg2.cuh): one block per SM, slice s -> block s % grid,
+// warp s / grid.  Picks the largest number of entry columns per slice (`wcap`, a multiple of 4) whose (col, w2)
+// pairs fit every block's shared memory; slices wider than that read their tail from global memory.
+ira_status plan_pcg2(ira_context* h) {
+  h->pcg2_ok = false;
+  if (h->pcg_blocks_per_sm <= 0 || h->nslices <= 0) return IRA_OK;
+  const int grid = std::min(h->nslices, h->sms);
+  if ((int64_t)grid * kPcg2Warps < h->nslices) return IRA_OK;          // more than one row per lane: k_pcg_persistent
+  h->h_slice_width.resize((size_t)h->nslices);
+  IRA_CUDA(h, cudaMemcpyAsync(h->h_slice_width.data(), h->slice_width.p, sizeof(int) * (size_t)h->nslices,
+                              cudaMemcpyDeviceToHost, h->stream));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  int wmax = 0;
+  for (int w : h->h_slice_width) wmax = std::max(wmax, w);
+  const int cap = (kPcg2SmemBudget - 24 * kPcg2Threads) / 12;          // entries of (int col, double w2) beside x
+  int wcap = wmax, need = 0;
+  for (;; wcap -= 4) {
+    need = 0;
+    for (int b = 0; b < grid; ++b) {
+      int e = 0;
+      for (int s = b; s < h->nslices; s += grid) e += std::min(h->h_slice_width[(size_t)s], wcap) * kSellC;
+      need = std::max(need, e);
+    }
+    if (need <= cap || wcap <= 0) break;
+  }
+  if (wcap < 4 && wmax >= 4) return IRA_OK;                            // nothing fits: not worth it
+  h->pcg2_wcap = std::max(wcap, 0);
+  h->pcg2_entries = std::max(need, kSellC);
+  const int bytes = h->pcg2_entries * 12 + 24 * kPcg2Threads;
+  if (cudaFuncSetAttribute(k_pcg_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return IRA_OK;
+  }
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_smem, kPcg2Threads, (size_t)bytes) != cudaSuccess || nb < 1) {
+    cudaGetLastError();
+    return IRA_OK;
+  }
+  h->pcg2_ok = true;
+  return IRA_OK;
+}
+
 ira_status upload_Q(ira_context* h, const double* Q, int64_t ld_q, DevBuf& dst) {
   const int n = h->n;
   if (n == 0) return IRA_OK;
@@ -946,6 +1005,8 @@ ira_status ira_problem_upload(ira_handle h, int64_t m, int64_t n_total, int32_t 
   if (!h->fmt_csr) {
     IRA_TRY(build_sell(h));
     if (h->sell_total > 3ll * std::max(h->nnz, 1) + 64ll * kSellSigma) h->fmt_csr = true;
+    h->pcg2_ok = false;
+    if (!h->fmt_csr && h->opt.world_size <= 1) IRA_TRY(plan_pcg2(h));
   }
   h->persistent = !h->fmt_csr && h->opt.world_size <= 1 && (h->opt.solver & 3) != 1 && h->pcg_blocks_per_sm > 0;
   h->peer = false;

@@ -27,11 +27,15 @@
 
 #include "ira.h"
 
-#if defined(__has_include)
-#if __has_include(<Eigen/Dense>)
-#include <Eigen/Dense>
+#if !defined(IROTAVG_HAVE_EIGEN) && defined(__has_include)
+#if __has_include(<Eigen/Dense>) && __has_include(<Eigen/Sparse>)
 #define IROTAVG_HAVE_EIGEN 1
 #endif
+#endif
+#ifdef IROTAVG_HAVE_EIGEN
+#include <Eigen/Dense>
+#include <Eigen/Geometry>
+#include <Eigen/Sparse>
 #endif
 
 // Define IROTAVG_B200_NO_REFERENCE_NAMES to get only namespace ira_b200 (templates over the caller's
@@ -56,9 +60,17 @@ inline std::ostream& operator<<(std::ostream& os, const Cost cost) {   /* ral/l1
 }
 
 #ifdef IROTAVG_HAVE_EIGEN
+// the reference's own typedefs, ral/l1_irls.hpp:43-50 (Long is SuiteSparse_long = long there)
+typedef long Long;
+typedef Eigen::SparseMatrix<double, Eigen::ColMajor, Long> SpMat;
 typedef Eigen::MatrixXd Mat;
 typedef Eigen::VectorXd Vec;
+typedef Eigen::Vector3d Vec3;
+typedef Eigen::Vector4d Vec4;
+typedef Eigen::Quaterniond Quat;
+typedef Eigen::Triplet<double> T;
 #else
+typedef long Long;
 // Minimal column-major stand-ins (only what the reference's callers touch).
 struct Mat {
   std::vector<double> v; long r = 0, c = 0;
@@ -86,6 +98,7 @@ struct Vec {
 };
 #endif
 
+#ifndef IROTAVG_HAVE_EIGEN
 // The sparse incidence matrix of the reference, as the two column indices of every row (-1 = none).
 struct SpMat {
   std::vector<int32_t> col_plus, col_minus;    // A(k, col_plus[k]) = +1, A(k, col_minus[k]) = -1
@@ -93,6 +106,7 @@ struct SpMat {
   long rows() const { return nrows; }
   long cols() const { return ncols; }
 };
+#endif
 
 }  // namespace irotavg
 #endif  // IROTAVG_B200_NO_REFERENCE_NAMES
@@ -115,6 +129,18 @@ inline void check(ira_status s, const char* what) {
   if (s != IRA_OK && s != IRA_ERR_NONFINITE) {
     std::cerr << what << " failed: " << ira_status_string(s) << ": " << ira_last_error(handle()) << std::endl;
     std::exit(-1);                                        // the reference's error behaviour
+  }
+}
+// The reference solves every linear step exactly (SuiteSparseQR / UMFPACK); this library iterates.  A solve
+// that stopped at cg_max_iters without reaching cg_rtol is therefore reported, never silent.
+inline ira_stats& stats() { static ira_stats st; return st; }
+inline void warn_unconverged(const char* what, const ira_stats& st) {
+  if (st.cg_hit_max > 0) {
+    double worst = 0.0;
+    for (int k = 0; k < st.irls_iters && k < IRA_STATS_MAX_ITERS; ++k) worst = st.cg_relres[k] > worst ? st.cg_relres[k] : worst;
+    std::cerr << "irotavg-b200 WARNING: " << what << ": " << st.cg_hit_max << " linear solve(s) stopped at the PCG iteration cap "
+              << "without reaching cg_rtol (worst relative residual " << worst << "); the step is inexact where the reference's "
+              << "is exact.  Raise ira_options.cg_max_iters." << std::endl;
   }
 }
 inline std::vector<int32_t> flatten(const I_t& I) {
@@ -151,9 +177,10 @@ inline void irls(const MatT& QQ, const I_t& I, const SpMatT& /*A*/, CostT cost, 
   int32_t it = 0;
   double rt = 0.0;
   ira_status s = ira_irls(detail::handle(), m, n, f, flat.data(), QQ.data(), m > 0 ? m : 1, Q.data(), n > 0 ? n : 1,
-                          (int32_t)cost, sigma, max_iters, change_th, weights.data(), &it, &rt, nullptr);
+                          (int32_t)cost, sigma, max_iters, change_th, weights.data(), &it, &rt, &detail::stats());
   if (s == IRA_ERR_UNKNOWN_COST) { std::cerr << "Unknown cost!!" << std::endl; std::exit(-1); }   // :723-726
   detail::check(s, "irls");
+  detail::warn_unconverged("irls", detail::stats());
   iteration = it;
   runtime = rt;
   if (it >= max_iters) std::cout << " Max Iteration" << std::endl;                                // :746-749
@@ -173,8 +200,9 @@ inline void l1ra(const MatT& QQ, const I_t& I, const SpMatT& /*A*/, MatT& Q, con
   int32_t it = 0;
   double rt = 0.0;
   ira_status s = ira_l1ra(detail::handle(), m, n, f, flat.data(), QQ.data(), m > 0 ? m : 1, Q.data(), n > 0 ? n : 1,
-                          max_iters, change_th, &it, &rt, nullptr);
+                          max_iters, change_th, &it, &rt, &detail::stats());
   detail::check(s, "l1ra");
+  detail::warn_unconverged("l1ra", detail::stats());
   iter = it;
   runtime = rt;
 }
@@ -207,7 +235,25 @@ inline void quat_normalised(MatT& Q, const int f) {
 
 #ifndef IROTAVG_B200_NO_REFERENCE_NAMES
 namespace irotavg {
+#ifdef IROTAVG_HAVE_EIGEN
+// The reference's SpMat, filled exactly like ral/l1_irls.cpp:755-780 from the rule ira_make_A restates
+// (row k: +1 at column j-f if j >= f; -1 at column i-f if additionally i >= f; a self-loop's second write wins).
+inline SpMat make_A(const int n, const int f, const I_t& I) {
+  const std::vector<int32_t> flat = ira_b200::detail::flatten(I);
+  std::vector<int32_t> cp(I.size()), cm(I.size());
+  ira_status s = ira_make_A((int64_t)I.size(), n, f, flat.data(), cp.data(), cm.data());
+  if (s != IRA_OK) { std::cerr << "make_A failed: " << ira_status_string(s) << std::endl; std::exit(-1); }
+  SpMat A((Long)I.size(), (Long)(n - f));
+  for (size_t k = 0; k < I.size(); ++k) {
+    if (cp[k] >= 0) A.coeffRef((Long)k, cp[k]) = 1;
+    if (cm[k] >= 0) A.coeffRef((Long)k, cm[k]) = -1;
+  }
+  A.makeCompressed();
+  return A;
+}
+#else
 inline SpMat make_A(const int n, const int f, const I_t& I) { return ira_b200::make_A_as<SpMat>(n, f, I); }
+#endif
 using ira_b200::irls;
 using ira_b200::l1ra;
 using ira_b200::init_mst;

@@ -21,9 +21,12 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <fstream>
+#include <iomanip>
 #include <iostream>
 #include <map>
 #include <set>
+#include <string>
 #include <type_traits>
 #include <vector>
 
@@ -65,6 +68,25 @@ inline void quat2rmat_rowmajor(const double qin[4], double R[9]) {
   R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
   R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
   R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+
+// ViewGraph::savePoses (src/ViewGraph.cpp:1206-1231): one line per view, "id \t qw \t qx \t qy \t qz \t tx \t ty \t tz",
+// quaternion from rmat2quat of the pose's rotation, 17 significant digits, scientific.  Returns false (after the
+// reference's "Unable to save results." on std::cerr) when the file cannot be opened.
+template <class ViewT>
+inline bool save_poses(const std::vector<ViewT*>& views, const std::string& filename) {
+  std::ofstream fs(filename);
+  if (!fs.is_open()) { std::cerr << "Unable to save results." << std::endl; return false; }
+  for (ViewT* view : views) {
+    const auto& pose = view->pose();
+    const auto& t = pose.t();
+    double q[4];
+    rmat2quat(pose.R(), q);
+    fs << view->frame().id() << "\t";
+    fs << std::setprecision(17) << std::scientific << q[3] << "\t" << q[0] << "\t" << q[1] << "\t" << q[2] << "\t";
+    fs << std::setprecision(17) << std::scientific << t(0) << "\t" << t(1) << "\t" << t(2) << "\n";
+  }
+  return true;
 }
 
 struct RotAvgReport {

@@ -273,6 +273,11 @@ class Matrix : public MatrixBase<Matrix> {
   CView leftCols(Index n) const { return v().leftCols(n); }
   Matrix& operator/=(double s) { for (double& x : d) x /= s; return *this; }
   Matrix& operator*=(double s) { for (double& x : d) x *= s; return *this; }
+  void transposeInPlace() {
+    Matrix t(c, r);
+    for (Index j = 0; j < c; ++j) for (Index i = 0; i < r; ++i) t.ref(j, i) = at(i, j);
+    d.swap(t.d); std::swap(r, c);
+  }
 };
 
 // Eigen::Map<Mat>: a column-major view over caller memory
@@ -379,6 +384,7 @@ typedef Matrix MatrixXd;
 typedef Matrix VectorXd;
 typedef Matrix Vector3d;
 typedef Matrix Vector4d;
+typedef Matrix Matrix3d;
 
 // ---- Quaternion (Eigen/src/Geometry/Quaternion.h, generic path) ----------------------------------------
 class Quaterniond {
@@ -400,6 +406,17 @@ class Quaterniond {
     const double z2 = squaredNorm();
     if (z2 > 0.0) { const double n = std::sqrt(z2); return Quaterniond(w_ / n, x_ / n, y_ / n, z_ / n); }
     return *this;
+  }
+  void normalize() { *this = normalized(); }
+  Matrix toRotationMatrix() const {         // Eigen/src/Geometry/Quaternion.h QuaternionBase::toRotationMatrix
+    Matrix res(3, 3);
+    const double tx = 2 * x_, ty = 2 * y_, tz = 2 * z_;
+    const double twx = tx * w_, twy = ty * w_, twz = tz * w_, txx = tx * x_, txy = ty * x_, txz = tz * x_;
+    const double tyy = ty * y_, tyz = tz * y_, tzz = tz * z_;
+    res(0, 0) = 1 - (tyy + tzz); res(0, 1) = txy - twz; res(0, 2) = txz + twy;
+    res(1, 0) = txy + twz; res(1, 1) = 1 - (txx + tzz); res(1, 2) = tyz - twx;
+    res(2, 0) = txz - twy; res(2, 1) = tyz + twx; res(2, 2) = 1 - (txx + tyy);
+    return res;
   }
 };
 

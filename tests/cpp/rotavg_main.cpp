@@ -2,7 +2,7 @@
 // ViewConnection, here the OpenCV-free stand-ins of view_shim.hpp) through ira_b200::rot_avg - the host
 // mirror of ViewGraph::rotAvg - and writes every view's rotation (row-major, 17 digits) followed by one
 // line per rotAvg call: "win solved vertices edges fixed l1_iters irls_iters seconds".
-//   rotavg_main ops.txt out.txt
+//   rotavg_main ops.txt out.txt [poses.txt]     (poses.txt: ira_b200::save_poses, the layout of ViewGraph::savePoses)
 #include <chrono>
 #include <cstdio>
 #include <fstream>
@@ -66,5 +66,6 @@ int main(int argc, char** argv) {
     out << calls[k].win << " " << (r.solved ? 1 : 0) << " " << r.vertices << " " << r.edges << " " << r.fixed << " "
         << r.l1_iters << " " << r.irls_iters << " " << calls[k].wall << "\n";
   }
+  if (argc > 3 && !ira_b200::save_poses(views, argv[3])) return 3;
   return 0;
 }

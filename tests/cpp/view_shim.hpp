@@ -12,6 +12,14 @@
 #include <utility>
 #include <vector>
 
+// OpenCV's core/cvdef.h macros (src/ViewGraph.cpp:1269 uses MIN)
+#ifndef MIN
+#define MIN(a, b) ((a) > (b) ? (b) : (a))
+#endif
+#ifndef MAX
+#define MAX(a, b) ((a) < (b) ? (b) : (a))
+#endif
+
 namespace cv {
 struct Matx33d {
   double val[9];
@@ -26,6 +34,12 @@ struct Vec3d {
   Vec3d(double a = 0, double b = 0, double c = 0) { val[0] = a; val[1] = b; val[2] = c; }
   double operator()(int i) const { return val[i]; }
 };
+struct Vec4d {
+  double val[4];
+  Vec4d(double a = 0, double b = 0, double c = 0, double d = 0) { val[0] = a; val[1] = b; val[2] = c; val[3] = d; }
+  double operator()(int i) const { return val[i]; }
+  double& operator()(int i) { return val[i]; }
+};
 struct DMatch { int queryIdx, trainIdx; };
 }  // namespace cv
 
@@ -35,6 +49,7 @@ class Pose {
  public:
   typedef cv::Matx33d Mat3;
   typedef cv::Vec3d Vec3;
+  typedef cv::Vec4d Vec4;
   Pose() : m_R(Mat3::eye()), m_t() {}
   Pose(Mat3 R, Vec3 t) : m_R(R), m_t(t) {}
   void setR(Mat3 R) { m_R = R; }
