@@ -3,28 +3,31 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cost L1]
 
-One *step* = one irls() call of 30 IRLS iterations (max_iters = 30, change_th = -1 so that all 30
-run; ral/l1_irls.cpp:590) on the synthetic random SO(3) graph n = 100 000 / m = 1 000 000
-(seed 20190319).
-  value      IRLS iterations / second, graph already resident in HBM (ira_irls_resident), device
-             time from CUDA events recorded on the library's launch stream, max over ranks.
-  e2e        the same metric through the host-buffer C-ABI call ira_irls(): pinned host buffers in,
-             H2D of (I, QQ, Q), CSR build, 30 iterations, D2H of (Q, weights) inside the timed region.
-  roofline   the dominant kernel (SpMV of the PCG solve): algorithmic bytes 16 m + 48 n per launch
-             over its mean launch duration measured with CUDA events around every SpMV launch of
-             a profiled step, against MEASURED_PEAKS.json's HBM copy bandwidth.
-  cpu_baseline  the oracle port (numpy/scipy restatement or, when built, the C restatement) timed
-             on the host cores on a bounded sample of the same call.
-N > 1 (launched by torchrun, one rank per GPU): WEAK scaling - the graph grows with the job, n = 100 000 N
-nodes / m = 1 000 000 N edges (same recipe and seed; N = 8 is configs[3]'s 1M-node / 10M-edge scale), the rows
-of the normal equations are partitioned over the ranks and one persistent kernel per rank runs each solve,
-exchanging through NVLink peer memory.  `value` = IRLS iterations/s x N, i.e. in units of the 1M-edge graph
-(edge-iterations per second / 1e6), so that perfect weak scaling reads N x the single-GPU value.  The line also
-carries `strong_scaling_1M_edges`: plain IRLS iterations/s of the SAME 1M-edge graph on N GPUs - at that size
-one PCG iteration (15 us of SpMV) is shorter than the two NVLink barrier latencies it needs, so it does not
-scale; DESIGN.md has the breakdown.
-`--impl reference` times the CPU port alone (the reference itself cannot be built here: no Eigen /
-SuiteSparse in the image).
+One *step* = one irls() call of 30 IRLS iterations (max_iters = 30, change_th = -1 so that all 30 run;
+ral/l1_irls.cpp:590) on the synthetic random SO(3) graph n = 100 000 / m = 1 000 000 (seed 20190319).
+  value      IRLS iterations / second, graph already resident in HBM (ira_irls_resident), device time from CUDA
+             events recorded on the library's launch stream, max over ranks.
+  e2e        the same metric through the host-buffer C-ABI call ira_irls(): pinned host buffers in, H2D of
+             (I, QQ, Q), CSR/SELL build, 30 iterations, D2H of (Q, weights) inside the timed region.
+  roofline   the dominant kernel = the persistent PCG kernel (one launch = one linear solve, >85 % of the step):
+             algorithmic bytes K (16 m + 224 n) per launch (SpMV 16m + 48n and CG vector work 176n per
+             PCG iteration, K = PCG iterations of that solve) over its mean launch duration from CUDA events recorded
+             on the launch stream around every launch of a profiled step, against MEASURED_PEAKS.json's HBM copy
+             bandwidth; the SpMV-only figure and the residual kernel (L2-warm and after an L2 flush) beside it.
+  cpu_baseline  the C restatement (oracle/irls_oracle.c) on the host cores, all cores and one core, on a bounded
+             sample of the same call; `config1_bundled_cli.reference_build` times oracle/_ref (the reference's own
+             ral/ sources) on the reference's bundled graph (configs[0]) beside this library on the same input.
+  parity     geodesic RMS of the timed run's final rotations against the committed 30-iteration golden of the C
+             restatement (tests/golden/cfg3_l1_30iters.npz) and of a 2-iteration run against the live oracle.
+N > 1 (torchrun, one rank per GPU): WEAK scaling - the graph grows with the job, n = 100 000 N / m = 1 000 000 N
+(same recipe and seed); rows of the normal equations partitioned over the ranks, one persistent kernel per rank
+exchanging through NVLink peer memory.  `value` = IRLS iterations/s x N (units of the 1M-edge graph), plain IRLS
+iterations/s on the N-times graph is `irls_iters_per_s_on_this_graph`.  Every N > 1 line carries the geodesic RMS of
+the N-GPU result against ONE GPU on the same graph and against the oracle (2 iterations), the strong-scaling figure
+of the 1M-edge graph and - at N = 8 - configs[3] at its stated size (n = 1M, m = 10M).
+`--impl reference` times the CPU restatement alone on the same workload (the reference's own solver stack - SPQR -
+cannot hold this graph: ~40 GB of fill; oracle/_ref, the reference's ral/ compiled against dense stand-ins, is limited
+to a few thousand edges), with the SAME bounded sample at every N: the first 10 IRLS iterations.
 """
 from __future__ import annotations
 
@@ -34,6 +37,7 @@ import os
 import statistics
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -49,6 +53,7 @@ SIGMA = 5 * np.pi / 180.0
 COSTS = {"L2": 0, "L1": 1, "L1.5": 2, "L0.5": 3, "Geman-McClure": 4, "Huber": 5}
 METRIC = "IRLS iters/sec on 1M-edge SO(3) graph"
 UNIT = "irls_iters/s"
+REF_SAMPLE_ITERS = 10           # --impl reference: the same iteration range at every N
 
 
 def measured_peak():
@@ -117,29 +122,20 @@ def make_graph(scale=1):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_port_run(g, cost, iters):
-    """Returns (irls_iters_per_s, kind, cores, sample_text, extra)."""
-    from oracle import irls_oracle as O
-    try:
-        from oracle import cport
-        have_c = cport.available()
-    except Exception:
-        have_c = False
-    if have_c:
-        threads = os.cpu_count() or 1
-        t0 = time.perf_counter()
-        r = cport.irls(g.QQ, g.I, cost, SIGMA, g.Q0, g.f, iters, -1.0, cg_rtol=1e-10, threads=threads)
-        dt = time.perf_counter() - t0
-        return iters / dt, "port", threads, (f"first {iters} of the 30 IRLS iterations of the same call (the later, costlier "
-                                             f"ones are left out to bound the run), C restatement oracle/irls_oracle.c, OpenMP "
-                                             f"{threads} threads, Jacobi-PCG rtol 1e-10; the reference's SuiteSparseQR solve "
-                                             "cannot run this graph: ~40 GB fill"), \
-            {"cg_iters": list(r["cg_iters"])}
+def cpu_port_run(g, cost, iters, threads=0):
+    """C restatement on `threads` cores (0 = all).  Returns (irls_iters_per_s, cores, result dict)."""
+    from oracle import cport
+    threads = threads or (os.cpu_count() or 1)
     t0 = time.perf_counter()
-    r = O.irls(g.QQ, g.I, None, cost, SIGMA, g.Q0, g.f, iters, -1.0, solver="pcg", pcg_rtol=1e-10)
+    r = cport.irls(g.QQ, g.I, cost, SIGMA, g.Q0, g.f, iters, -1.0, cg_rtol=1e-10, threads=threads)
     dt = time.perf_counter() - t0
-    return iters / dt, "port", 1, (f"first {iters} of the 30 IRLS iterations of the same call, numpy/scipy restatement "
-                                   "(oracle/irls_oracle.py, 1 thread, Jacobi-PCG rtol 1e-10)"), {"cg_iters": r.cg_iters}
+    return iters / dt, threads, r
+
+
+def cpu_sample_text(iters, threads):
+    return (f"first {iters} of the 30 IRLS iterations of the same call (the later, costlier ones are left out to bound the "
+            f"run), C restatement oracle/irls_oracle.c, OpenMP {threads} thread(s), Jacobi-PCG rtol 1e-10; the reference's "
+            "SuiteSparseQR solve cannot run this graph (~40 GB fill) and oracle/_ref is dense (few thousand edges)")
 
 
 def run_reference_arm(args):
@@ -149,26 +145,24 @@ def run_reference_arm(args):
     scale = max(1, args.gpus)                      # the same workload as our arm at N GPUs (weak scaling: graph x N)
     g = make_graph(scale)
     cost = COSTS[args.cost]
-    # bounded sample: the first 10 IRLS iterations up to 2M edges, fewer on the larger graphs (a CPU step must stay
-    # under a minute): 10, 10, 5, 4 iterations at x1, x2, x4, x8
-    sample_iters = max(4, min(args.ref_iters, (2 * args.ref_iters) // scale))
     for _ in range(min(args.warmup, 1)):
         cpu_port_run(g, cost, 1)
-    vals = []
-    extra = {}
-    kind, cores, sample = "port", 1, ""
+    cores = os.cpu_count() or 1
+    cg = []
     t_all = time.perf_counter()
     for _ in range(args.steps):
-        v, kind, cores, sample, extra = cpu_port_run(g, cost, sample_iters)
-        vals.append(v)
+        _, cores, r = cpu_port_run(g, cost, REF_SAMPLE_ITERS)
+        cg = list(r["cg_iters"])
     dt = time.perf_counter() - t_all
-    value = scale * sample_iters * args.steps / dt          # units of the 1M-edge graph, like our arm
+    value = scale * REF_SAMPLE_ITERS * args.steps / dt          # units of the 1M-edge graph, like our arm
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, scale),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, **extra},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": cpu_sample_text(REF_SAMPLE_ITERS, cores) + "; the same 10-iteration sample at every N",
+                         "cg_iters": cg},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -177,7 +171,7 @@ def run_reference_arm(args):
 
 def workload_config(args, scale, world=None):
     world = scale if world is None else world
-    tag = "configs[2]" if scale == 1 else f"configs[2] recipe scaled x{scale} (weak scaling; x8 = configs[3] scale)"
+    tag = "configs[2]" if scale == 1 else f"configs[2] recipe scaled x{scale} (weak scaling; x10 on 8 GPUs = configs[3])"
     return {
         "workload": f"{tag}: synthetic random SO(3) graph n={N_NODES * scale} m={M_EDGES * scale} (path + uniform pairs, "
                     f"sigma_n=0.05 rad, 10% outliers, seed 20190319), {IRLS_ITERS} IRLS iters per step, cost {args.cost}, "
@@ -185,11 +179,108 @@ def workload_config(args, scale, world=None):
         "cost": args.cost, "irls_iters_per_step": IRLS_ITERS, "cg_rtol": 1e-10,
         "parallelism": "single GPU" if world == 1 else (
             f"rows of A^T D^2 A partitioned over {world} ranks, one persistent PCG kernel per rank exchanging u slices / "
-            "dot products / barrier flags through NVLink peer memory (CUDA IPC); edge kernels replicated"
+            "dot products through NVLink peer memory (CUDA IPC); edge kernels replicated"
             if getattr(args, "shard_mode", 0) == 1 else
             f"edges sharded over {world} ranks, NCCL all-reduce of node vectors per PCG iteration"),
         "l2": "512 MB memset between timed steps flushes L2 (working set ~150 MB also exceeds the 126 MB L2)",
     }
+
+
+# ------------------------------------------------------------------------------------------------
+# extra legs of the N = 1 line (each guarded: the headline line must never depend on them)
+# ------------------------------------------------------------------------------------------------
+def guarded(fn):
+    try:
+        return fn()
+    except Exception as e:                                   # noqa: BLE001
+        return {"error": repr(e)[:300]}
+
+
+def leg_config2(ira, local_rank):
+    """configs[1]: KITTI-00-scale view graph (n = 4 541, m = 50 000), 30 IRLS iterations, L1 and Geman-McClure,
+    beside the oracle's sparse DIRECT solve of the normal equations on one host core ('restatement, direct' -
+    the formulation the reference's SPQR is comparable with at this size)."""
+    from oracle import graphs as G
+    from oracle import irls_oracle as O
+    g = G.kitti_like_graph()
+    out = {"workload": f"configs[1]: kitti_like_graph n={g.n} m={g.m}, {IRLS_ITERS} IRLS iterations, change_th=-1"}
+    with ira.Solver(device=local_rank) as s:
+        s.upload(g.QQ, g.I, g.Q0, g.f)
+        for nm in ("L1", "Geman-McClure"):
+            s.irls_resident(COSTS[nm], SIGMA, IRLS_ITERS, -1.0)
+            best, info = None, None
+            for _ in range(3):
+                info = s.irls_resident(COSTS[nm], SIGMA, IRLS_ITERS, -1.0)
+                best = info.device_ms if best is None else min(best, info.device_ms)
+            Q, _ = s.download()
+            t0 = time.perf_counter()
+            ref = O.irls(g.QQ, g.I, None, COSTS[nm], SIGMA, g.Q0, g.f, IRLS_ITERS, -1.0, solver="direct")
+            cpu_s = time.perf_counter() - t0
+            out[nm] = {"value": IRLS_ITERS / (best / 1e3), "unit": UNIT, "ms_per_step": best,
+                       "cg_iters_per_step": int(sum(info.cg_iters)),
+                       "cpu_baseline": {"value": IRLS_ITERS / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
+                                        "sample": "all 30 iterations, oracle/irls_oracle.py with scipy's sparse LU of A^T D^2 A "
+                                                  "(restatement, direct)"},
+                       "geodesic_rms_vs_oracle_30iters_rad": float(O.geodesic_rms(Q, ref.Q, g.f))}
+    return out
+
+
+def leg_bundled(ira, local_rank):
+    """configs[0]: the reference's own CLI flow on its bundled graph - oracle/_ref (the reference's ral/ sources) on the
+    host cores beside this library's CLI binary on the GPU, same input file, outputs compared."""
+    from oracle import build_ref, refbin
+    from oracle import graphs as G
+    from oracle import irls_oracle as O
+    from irotavg_b200 import build
+    b = np.load(os.path.join(ROOT, "tests", "golden", "bundled_graph.npz"))
+    td = tempfile.mkdtemp()
+    inp = os.path.join(td, "ravg_input.txt")
+    G.write_ral_text(inp, b["I"] + 1, b["QQ"], b["Q_file"][: int(b["n_given"])], int(b["f"]))
+    cli = build.build_cli()
+    ours = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        subprocess.run([cli, inp, os.path.join(td, "ours.txt")], check=True, capture_output=True)
+        ours.append(time.perf_counter() - t0)
+    n, m = 1832, 3655
+    Qo, _ = refbin.read_cli_output(os.path.join(td, "ours.txt"), n, m)
+    out = {"workload": "configs[0]: ral/data/ravg_input.txt (n=1832, m=3655), CLI default flow init_mst -> l1ra(5) -> "
+                       "irls(Geman-McClure, 50) -> quat_normalised, whole process incl. file I/O and CUDA context creation",
+           "ours_process_s": min(ours)}
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "ref_bundled_cli.npz"))
+    out["geodesic_rms_vs_reference_golden_rad"] = float(O.geodesic_rms(Qo, gold["default_Q"], 1))
+    if build_ref.built():
+        t0 = time.perf_counter()
+        r = refbin.cli([inp, os.path.join(td, "ref.txt")])
+        dt = time.perf_counter() - t0
+        if r.returncode == 0:
+            Qr, _ = refbin.read_cli_output(os.path.join(td, "ref.txt"), n, m)
+            out["reference_build"] = {"process_s": dt, "kind": "reference", "cores": os.cpu_count(),
+                                      "reported": [l for l in r.stdout.splitlines() if "runtime" in l],
+                                      "note": "oracle/_ref = ral/test.cpp + ral/l1_irls.cpp compiled unmodified; its SPQR / "
+                                              "UMFPACK are DENSE stand-ins (oracle/ref_shim), so this time is not SuiteSparse's",
+                                      "geodesic_rms_ours_vs_live_reference_rad": float(O.geodesic_rms(Qo, Qr, 1))}
+    with ira.Solver(device=local_rank) as s:             # the solve alone through the library call (host buffers)
+        args = (b["QQ"], b["I"], b["Q_mst"], int(b["f"]), 5, 1e-3, COSTS["Geman-McClure"], SIGMA, 50, 1e-3)
+        s.l1ra_irls(*args)
+        t0 = time.perf_counter()
+        s.l1ra_irls(*args)
+        out["ours_l1ra_irls_call_ms"] = 1e3 * (time.perf_counter() - t0)
+    return out
+
+
+def leg_aux(ira, local_rank, g):
+    """init_mst on the headline graph (device) beside one host core running the literal sweep (C restatement)."""
+    from oracle import irls_oracle as O
+    with ira.Solver(device=local_rank) as s:
+        s.upload(g.QQ, g.I, g.Q0, g.f)
+        s.init_mst_resident(g.f)
+        st = s.init_mst_resident(g.f)
+    t0 = time.perf_counter()
+    O.init_mst(g.Q0, g.QQ, g.I, g.f)
+    cpu = time.perf_counter() - t0
+    return {"init_mst_device_ms": st["ms"], "passes_label": st["passes_label"], "passes_propagate": st["passes_propagate"],
+            "init_mst_oracle_1core_ms": 1e3 * cpu}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -261,22 +352,25 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def timed_resident(c, reps):
+        """reps timed resident steps of `s` (L2 flushed before each, CUDA events on the launch stream)."""
+        ms, info = 0.0, None
+        for _ in range(reps):
+            with torch.cuda.stream(ext):
+                flush.zero_()                                    # L2 flush, outside the event pair
+                a = torch.cuda.Event(enable_timing=True)
+                b = torch.cuda.Event(enable_timing=True)
+                a.record(ext)
+                info = s.irls_resident(c, SIGMA, IRLS_ITERS, -1.0)
+                b.record(ext)
+            b.synchronize()
+            ms += a.elapsed_time(b)
+        return ms, info
+
     # ---- resident arm (value) -----------------------------------------------------------------
     s.upload(QQ_loc, I_loc, g.Q0, f)
-
-    def resident_step():
-        with torch.cuda.stream(ext):
-            flush.zero_()                                    # L2 flush, outside the event pair
-            a = torch.cuda.Event(enable_timing=True)
-            b = torch.cuda.Event(enable_timing=True)
-            a.record(ext)
-            info = s.irls_resident(cost, SIGMA, IRLS_ITERS, -1.0)
-            b.record(ext)
-        b.synchronize()
-        return a.elapsed_time(b), info
-
     for _ in range(args.warmup):
-        resident_step()
+        timed_resident(cost, 1)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -284,7 +378,7 @@ def run_ours(args):
     t_wall0 = time.perf_counter()
     dev_ms, launches, infos = 0.0, 0, []
     for _ in range(args.steps):
-        ms, info = resident_step()
+        ms, info = timed_resident(cost, 1)
         dev_ms += ms
         launches += info.kernel_launches
         infos.append(info)
@@ -303,24 +397,50 @@ def run_ours(args):
             continue
         s.irls_resident(COSTS[nm], SIGMA, IRLS_ITERS, -1.0)
         barrier()
-        ms = 0.0
-        for _ in range(2):
-            with torch.cuda.stream(ext):
-                flush.zero_()
-                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-                a.record(ext)
-                oi = s.irls_resident(COSTS[nm], SIGMA, IRLS_ITERS, -1.0)
-                b.record(ext)
-            b.synchronize()
-            ms += a.elapsed_time(b)
+        ms, oi = timed_resident(COSTS[nm], 2)
         ms = max_over_ranks(ms)
         other[nm] = {"value": world_units * IRLS_ITERS * 2 / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms / 2,
                      "cg_iters_per_step": int(sum(oi.cg_iters))}
 
-    # ---- N > 1: the same 1M-edge graph on N GPUs (strong scaling), 1 warm-up + 2 timed steps ------------
-    strong = None
+    # ---- N > 1: parity of the N-GPU result, strong scaling, configs[3] at full size ---------------------------------
+    multi = {}
     if world > 1:
-        try:                                             # an extra: it must never cost the headline line
+        from oracle import irls_oracle as O
+
+        def identical_on_all_ranks(Q):
+            t = torch.from_numpy(np.ascontiguousarray(Q)).cuda()
+            t0 = t.clone()
+            dist.broadcast(t0, 0)
+            return bool(max_over_ranks(0.0 if torch.equal(t, t0) else 1.0) == 0.0)
+        multi["bitwise_identical_across_ranks"] = identical_on_all_ranks(Q_res)
+        # (1) the same graph, the same 30 iterations, on ONE GPU (rank 0 only; the other ranks wait at the barrier)
+        if rank == 0:
+            try:
+                with ira.Solver(device=local_rank) as s1:
+                    s1.upload(g.QQ, g.I, g.Q0, f)
+                    t1 = s1.irls_resident(cost, SIGMA, IRLS_ITERS, -1.0).device_ms
+                    i1 = s1.irls_resident(cost, SIGMA, IRLS_ITERS, -1.0)
+                    Q1, _ = s1.download()
+                one_ms = min(t1, i1.device_ms)
+                multi["geodesic_rms_vs_one_gpu_same_graph_30iters_rad"] = float(O.geodesic_rms(Q_res, Q1, f))
+                multi["one_gpu_same_graph"] = {"ms_per_step": one_ms, "cg_iters_per_step": int(sum(i1.cg_iters)),
+                                               "speedup_of_n_gpus": one_ms / (dev_ms / args.steps)}
+            except Exception as e:                           # noqa: BLE001
+                multi["one_gpu_same_graph"] = {"error": repr(e)[:300]}
+        barrier()
+        # (2) 2 iterations against the CPU oracle (C restatement, Jacobi-PCG rtol 1e-12) on rank 0
+        try:
+            s.irls_resident(cost, SIGMA, 2, -1.0)
+            Q2, _ = s.download()
+            if rank == 0:
+                from oracle import cport
+                r = cport.irls(g.QQ, g.I, cost, SIGMA, g.Q0, f, 2, -1.0, cg_rtol=1e-12, threads=os.cpu_count() or 1)
+                multi["geodesic_rms_vs_oracle_2iters_rad"] = float(O.geodesic_rms(Q2, r["Q"], f))
+        except Exception as e:                               # noqa: BLE001
+            multi["geodesic_rms_vs_oracle_2iters_rad"] = repr(e)[:300]
+        barrier()
+        # (3) strong scaling: the SAME 1M-edge graph on N GPUs (below peer_min_rows: every rank solves it alone)
+        try:
             g1 = make_graph(1)
             if shard_mode == 1:
                 s.upload(g1.QQ, g1.I, g1.Q0, g1.f)
@@ -329,24 +449,44 @@ def run_ours(args):
                 s.upload(np.asfortranarray(g1.QQ[lo1:hi1]), np.ascontiguousarray(g1.I[lo1:hi1]), g1.Q0, g1.f)
             s.irls_resident(cost, SIGMA, IRLS_ITERS, -1.0)
             barrier()
-            ms = 0.0
-            for _ in range(2):
-                with torch.cuda.stream(ext):
-                    flush.zero_()
-                    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-                    a.record(ext)
-                    si = s.irls_resident(cost, SIGMA, IRLS_ITERS, -1.0)
-                    b.record(ext)
-                b.synchronize()
-                ms += a.elapsed_time(b)
+            ms, si = timed_resident(cost, 2)
             ms = max_over_ranks(ms)
-            ph = si.profile.get("pcg_phases") or {}
-            strong = {"value": IRLS_ITERS * 2 / (ms / 1000.0), "unit": "irls_iters/s (n=100000, m=1000000)",
-                      "ms_per_step": ms / 2, "cg_iters_per_step": int(sum(si.cg_iters)),
-                      "pcg_us_per_iteration": 1e3 * ph.get("kernel_ms", 0.0) / max(1, int(sum(si.cg_iters)))}
+            multi["strong_scaling_1M_edges"] = {
+                "value": IRLS_ITERS * 2 / (ms / 1000.0), "unit": "irls_iters/s (n=100000, m=1000000)", "ms_per_step": ms / 2,
+                "cg_iters_per_step": int(sum(si.cg_iters)),
+                "note": "n < ira_options.peer_min_rows (120000): not partitioned, every rank runs the single-GPU kernels"}
             del g1
-        except Exception as e:
-            strong = {"error": repr(e)}
+        except Exception as e:                               # noqa: BLE001
+            multi["strong_scaling_1M_edges"] = {"error": repr(e)[:300]}
+        # (4) N = 8: configs[3] at its stated size, n = 1 000 000 / m = 10 000 000
+        if world == 8 and gscale == 8 and shard_mode == 1 and not args.no_config3:
+            try:
+                g10 = make_graph(10)
+                s.upload(g10.QQ, g10.I, g10.Q0, g10.f)
+                s.irls_resident(cost, SIGMA, IRLS_ITERS, -1.0)
+                barrier()
+                ms, ci = timed_resident(cost, 2)
+                ms = max_over_ranks(ms)
+                Q10, _ = s.download()
+                c3 = {"workload": "configs[3]: n=1000000 m=10000000, 30 IRLS iterations, L1", "ms_per_step": ms / 2,
+                      "irls_iters_per_s": IRLS_ITERS * 2 / (ms / 1000.0),
+                      "value_in_1M_edge_units": 10 * IRLS_ITERS * 2 / (ms / 1000.0),
+                      "cg_iters_per_step": int(sum(ci.cg_iters)), "cg_hit_max": int(ci.cg_hit_max),
+                      "final_score": ci.scores[-1] if ci.scores else None,
+                      "bitwise_identical_across_ranks": identical_on_all_ranks(Q10)}
+                s.irls_resident(cost, SIGMA, 2, -1.0)
+                Q2, _ = s.download()
+                if rank == 0:
+                    from oracle import cport
+                    r = cport.irls(g10.QQ, g10.I, cost, SIGMA, g10.Q0, g10.f, 2, -1.0, cg_rtol=1e-12,
+                                   threads=os.cpu_count() or 1)
+                    c3["geodesic_rms_vs_oracle_2iters_rad"] = float(O.geodesic_rms(Q2, r["Q"], g10.f))
+                    c3["geodesic_rms_vs_ground_truth_rad"] = float(O.geodesic_rms(Q10, g10.Qgt, g10.f))
+                multi["configs3_full_size"] = c3
+                del g10
+            except Exception as e:                           # noqa: BLE001
+                multi["configs3_full_size"] = {"error": repr(e)[:300]}
+            barrier()
         s.upload(QQ_loc, I_loc, g.Q0, f)
 
     # ---- e2e arm: host-buffer C-ABI call, pinned buffers --------------------------------------
@@ -391,19 +531,22 @@ def run_ours(args):
     roof = None
     prof_share = None
     if world == 1 and gscale == 1:
-        # (1) the SpMV inside the timed solve: block 0's in-kernel clocks of the persistent PCG kernel
         info = infos[-1]
-        ph = info.profile.get("pcg_phases")
-        # (2) the same SpMV code as a stand-alone kernel, CUDA events on the launch stream
-        sp = ira.Solver(device=local_rank, profile=True, solver=1)
+        ph = info.profile.get("pcg_phases") or {}
+        # CUDA events around EVERY kernel launch of one more step of the same call (profile mode)
+        sp = ira.Solver(device=local_rank, profile=True)
         sp.upload(QQ_loc, I_loc, g.Q0, f)
-        pinfo = sp.irls_resident(COSTS["Geman-McClure"], SIGMA, 6, -1.0)   # events around every launch
+        sp.irls_resident(cost, SIGMA, IRLS_ITERS, -1.0)
+        pinfo = sp.irls_resident(cost, SIGMA, IRLS_ITERS, -1.0)
         pr = pinfo.profile
         tot = sum(v["ms"] for v in pr.values() if "launches" in v)
         prof_share = {k: round(v["ms"] / tot, 4) for k, v in pr.items() if "launches" in v}
-        spmv_us = sp.time_kernel(1, 200, False)
+        pcg = pr.get("pcg", {"ms": 0.0, "launches": 1})
+        K = sum(pinfo.cg_iters) / max(1, pcg["launches"])                      # PCG iterations per launch (mean)
+        per_iter_bytes = 16 * m + 224 * n                                       # SpMV + CG vector work
+        launch_us = 1e3 * pcg["ms"] / max(1, pcg["launches"])
+        ach = K * per_iter_bytes / (launch_us * 1e-6) / 1e9 if launch_us > 0 else 0.0
         res_us = sp.time_kernel(0, 100, False)
-        spmv_cold = sp.time_kernel(1, 20, True)
         res_cold = sp.time_kernel(0, 20, True)
         sp.close()
         spmv_bytes = 16 * m + 48 * n
@@ -413,19 +556,24 @@ def run_ours(args):
         if os.path.exists(tp):
             with open(tp) as fh:
                 traffic = json.load(fh)
-        ach = spmv_bytes / (spmv_us * 1e-6) / 1e9
+        spmv_phase_us = ph.get("spmv_us_per_phase")
         roof = {
-            "kernel": "k_spmv_sell (A^T D^2 A p, 3 RHS, SELL-32 thread-per-row)", "bound": "hbm", "achieved": ach,
-            "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
-            "traffic": (traffic or {}).get("k_spmv_sell"), "algorithmic_bytes_per_launch": spmv_bytes,
-            "launch_us": spmv_us, "launches_timed": 200,
-            "note": "launch_us = CUDA events on the launch stream around 200 back-to-back launches, L2-warm as inside the "
-                    "PCG loop (the ~100 MB the kernel touches stays L2-resident between PCG iterations); cold_l2_us = same "
-                    "kernel after a 512 MB L2 flush.  The kernel is bound by L2 sector bandwidth of the 2m random 32 B "
-                    "gathers (tools/microbench.cu: 2M gathers alone take >= 10.4 us), not by HBM.",
-            "cold_l2_us": spmv_cold,
-            "in_solve_phase_us": (ph or {}).get("spmv_us_per_phase"),
-            "in_solve_share_of_pcg_kernel": (ph["spmv_ms"] / ph["kernel_ms"]) if ph else None,
+            "kernel": "k_pcg_smem (persistent PCG solve: SELL SpMV with the matrix in shared memory + Chronopoulos-Gear PCG, "
+                      "3 RHS; one launch per IRLS iteration)",
+            "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "peak_source": peak_src, "traffic": (traffic or {}).get("k_pcg_smem"),
+            "algorithmic_bytes_per_launch": K * per_iter_bytes, "algorithmic_bytes_per_pcg_iteration": per_iter_bytes,
+            "pcg_iterations_per_launch": K, "launch_us": launch_us, "launches_timed": pcg["launches"],
+            "share_of_step": prof_share.get("pcg"),
+            "us_per_pcg_iteration": launch_us / max(K, 1e-9),
+            "note": "launch_us = CUDA events on the launch stream around each of the 30 PCG-kernel launches of one step "
+                    "(profile mode, same call as the timed steps).  The kernel's data (matrix in shared memory, u in L2) never "
+                    "leaves the chip between PCG iterations, so the HBM roofline is a bound it cannot reach: the SpMV phase "
+                    "sits on the L2 sector bandwidth of the 2m random 32 B gathers (tools/microbench.cu: >= 10.4 us), the rest "
+                    "is two grid barriers per iteration.",
+            "spmv_phase": {"us_per_phase_incl_reduction": spmv_phase_us, "algorithmic_bytes": spmv_bytes,
+                           "frac_spmv_bytes_only": (spmv_bytes / (spmv_phase_us * 1e-6) / 1e9 / peak) if spmv_phase_us else None,
+                           "frac_of_l2_gather_ceiling_10p4us": (10.4 / spmv_phase_us) if spmv_phase_us else None},
             "residual_kernel": {"launch_us": res_us, "algorithmic_bytes_per_launch": res_bytes,
                                 "achieved": res_bytes / (res_us * 1e-6) / 1e9,
                                 "frac": res_bytes / (res_us * 1e-6) / 1e9 / peak,
@@ -433,38 +581,39 @@ def run_ours(args):
                                 "traffic": (traffic or {}).get("k_residual")},
         }
 
-    # ---- parity against the oracle on the run itself (bounded: the first 2 iterations) ----------
+    # ---- parity against the oracle on the run itself ----------------------------------------------
     cpu = None
-    rms = None
+    rms = rms30 = dev30 = None
     if rank == 0 and world == 1 and gscale == 1:
         from oracle import irls_oracle as O
-        v, kind, cores, sample, extra = cpu_port_run(g, cost, args.ref_iters)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+        v, cores, r = cpu_port_run(g, cost, args.ref_iters)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample_text(args.ref_iters, cores),
+               "cg_iters": list(r["cg_iters"])}
+        v1, _, _ = cpu_port_run(g, cost, 3, threads=1)
+        cpu["single_thread"] = {"value": v1, "unit": UNIT, "cores": 1, "sample": cpu_sample_text(3, 1)}
         ref = O.irls(g.QQ, g.I, None, cost, SIGMA, g.Q0, f, 2, -1.0, solver="pcg", pcg_rtol=1e-13)
         s2 = ira.Solver(device=local_rank)
         Q2, _, _ = s2.irls(g.QQ, g.I, None, cost, SIGMA, g.Q0, f, 2, -1.0)
         s2.close()
         rms = O.geodesic_rms(Q2, ref.Q, f)
+        gpath = os.path.join(ROOT, "tests", "golden", "cfg3_l1_30iters.npz")
+        if args.cost == "L1" and os.path.exists(gpath):       # all 30 iterations of the timed run itself
+            gold = np.load(gpath)
+            rms30 = O.geodesic_rms(Q_res, gold["Q"], f)
+            dev30 = float(np.abs(np.array(infos[-1].scores) / gold["scores"] - 1).max())
 
-    # ---- parity of the timed run itself: all 30 iterations against the committed golden of the C restatement ----
-    rms30 = dev30 = None
-    gpath = os.path.join(ROOT, "tests", "golden", "cfg3_l1_30iters.npz")
-    if rank == 0 and world == 1 and gscale == 1 and args.cost == "L1" and os.path.exists(gpath):
-        from oracle import irls_oracle as O
-        gold = np.load(gpath)
-        rms30 = O.geodesic_rms(Q_res, gold["Q"], f)
-        dev30 = float(np.abs(np.array(infos[-1].scores) / gold["scores"] - 1).max())
-
-    # ---- configs[4] (incremental rotAvg stream), bounded sample: first 1500 frames of the 10k-frame stream -------
-    stream = None
-    if rank == 0 and world == 1 and gscale == 1 and not args.no_stream:
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import bench_stream
-            stream = bench_stream.run(frames=1500, loop_every=500, cpu_frames=40)
-            stream["sample"] = "first 1500 frames of the 10 000-frame stream (tools/bench_stream.py runs all of it)"
-        except Exception as e:                           # the headline line must not depend on g++ being present
-            stream = {"error": repr(e)}
+    # ---- the other configs (bounded), N = 1 only ------------------------------------------------------------
+    extras = {}
+    if rank == 0 and world == 1 and gscale == 1 and not args.no_extras:
+        extras["config2_kitti_scale"] = guarded(lambda: leg_config2(ira, local_rank))
+        extras["config1_bundled_cli"] = guarded(lambda: leg_bundled(ira, local_rank))
+        extras["init_mst"] = guarded(lambda: leg_aux(ira, local_rank, g))
+        if not args.no_stream:
+            def stream():
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import bench_stream
+                return bench_stream.run(frames=args.stream_frames, loop_every=500, cpu_frames=40)
+            extras["config5_rotavg_stream"] = guarded(stream)
 
     if rank == 0:
         info = infos[-1]
@@ -478,27 +627,25 @@ def run_ours(args):
                     "bitwise_equal_to_resident": same},
             "gpu_launches": int(launches), "clocks": clocks,
             "wall_ms_per_step": wall_ms / args.steps,
+            "irls_iters_per_s_on_this_graph": IRLS_ITERS * args.steps / (dev_ms / 1000.0),
             "cg_iters_per_step": int(sum(info.cg_iters)), "cg_hit_max": int(info.cg_hit_max),
             "final_score": info.scores[-1] if info.scores else None,
-            "geodesic_rms_vs_oracle_2iters_rad": rms,
+            "geodesic_rms_vs_oracle_2iters_rad": rms if world == 1 else multi.pop("geodesic_rms_vs_oracle_2iters_rad", None),
             "geodesic_rms_vs_oracle_30iters_rad": rms30, "max_score_rel_dev_vs_oracle_30iters": dev30,
         }
         if roof is not None:
             line["roofline"] = roof
-            line["kernel_time_share_multikernel_path"] = prof_share
+            line["kernel_time_share"] = prof_share
         if other:
             line["other_costs"] = other
-        if strong is not None:
-            line["strong_scaling_1M_edges"] = strong
         if gscale > 1:
             line["value_note"] = (f"weak scaling: the graph is the configs[2] recipe x{gscale} ({m} edges); value = IRLS "
-                                  f"iterations/s x {gscale}, i.e. in units of the 1M-edge graph; plain IRLS iterations/s on "
-                                  f"this graph = value / {gscale}")
+                                  f"iterations/s x {gscale}, i.e. in units of the 1M-edge graph")
         if world > 1:
             ph = info.profile.get("pcg_phases") or {}
             line["pcg_us_per_iteration"] = 1e3 * ph.get("kernel_ms", 0.0) / max(1, int(sum(info.cg_iters)))
-        if stream is not None:
-            line["config5_rotavg_stream"] = stream
+            line.update(multi)
+        line.update(extras)
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -519,7 +666,10 @@ def main():
     ap.add_argument("--graph-scale", type=int, default=0,
                     help="graph = configs[2] recipe x this (default: the number of GPUs); e.g. --gpus 1 --graph-scale 8 "
                          "runs the 8-GPU workload on one GPU for comparison")
-    ap.add_argument("--no-stream", action="store_true", help="skip the bounded configs[4] rotAvg-stream sample")
+    ap.add_argument("--no-stream", action="store_true", help="skip the configs[4] rotAvg stream")
+    ap.add_argument("--stream-frames", type=int, default=10000, help="frames of the configs[4] stream (all 10 000 by default)")
+    ap.add_argument("--no-extras", action="store_true", help="N = 1: skip the configs[0] / [1] / [4] and init_mst legs")
+    ap.add_argument("--no-config3", action="store_true", help="N = 8: skip configs[3] at full size")
     ap.add_argument("--ref-iters", type=int, default=10, help="IRLS iterations in the CPU port's bounded sample")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -85,7 +85,11 @@ typedef struct ira_options {
                               loads and stores into the peers' HBM over NVLink (CUDA IPC mappings,
                               irotavg_b200/csrc/ira_peer.cuh); weights come back whole on every rank.  1 = barrier-free
                               exchange (self-validating data), 2 = the same with two cross-GPU barriers per iteration */
-  int32_t reserved[3];
+  int32_t peer_min_rows;   /* world_size > 1, shard_mode 1 / 2: a graph with fewer nodes than this is NOT partitioned -
+                              every rank solves the whole problem itself with the single-GPU kernels (bitwise
+                              identical results, no exchange): below ~10^5 rows one PCG iteration is shorter than the
+                              NVLink latencies a partitioned iteration needs.  Default 120000; 0 = always partition */
+  int32_t reserved[2];
   double  pair_theta3;     /* a still-single node joins the pair holding its strongest neighbour when that edge's
                               normalised strength is >= pair_theta3 (3x3 blocks, inverted exactly); 0 = pairs only.
                               Default 0.05                                                                      */
@@ -158,7 +162,10 @@ ira_status ira_problem_download(ira_handle h, double* Q, int64_t ld_q, double* w
  * 228-468, two Newton steps each), whose Newton systems A'^T diag(sigx) A' dx = w1p (UMFPACK LU in the
  * reference) are solved by the persistent PCG kernel.  Q rows [f, n_total) are updated in place;
  * *iters_out / *runtime_s_out are the reference's `iter` / `runtime`.  stats->score[] holds the outer
- * scores, stats->cg_iters[] the Newton-PCG iterations per outer iteration.  Single GPU. */
+ * scores, stats->cg_iters[] the Newton-PCG iterations per outer iteration.  Works on every graph irls accepts
+ * (hub graphs whose SELL padding made irls choose its CSR kernels included: the stage walks the SELL copy anyway,
+ * slowly on the hub rows).  world_size > 1: every rank runs it on its whole-graph copy (shard_mode 1 / 2), with
+ * bitwise identical results on all ranks; edge shards (shard_mode 0) return IRA_ERR_INVALID_ARG. */
 ira_status ira_l1ra(ira_handle h, int64_t m, int64_t n_total, int32_t f,
                     const int32_t* I_pairs, const double* QQ, int64_t ld_qq,
                     double* Q, int64_t ld_q, int32_t max_iters, double change_th,

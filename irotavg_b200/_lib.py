@@ -39,7 +39,8 @@ class Options(C.Structure):
         ("spmv_variant", C.c_int32),
         ("small_path", C.c_int32),
         ("shard_mode", C.c_int32),
-        ("reserved", C.c_int32 * 3),
+        ("peer_min_rows", C.c_int32),
+        ("reserved", C.c_int32 * 2),
         ("pair_theta3", C.c_double),
     ]
 

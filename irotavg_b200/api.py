@@ -82,7 +82,7 @@ class Solver:
                  cg_check_every: int | None = None, lanes_per_row: int = 0, world_size: int = 1,
                  rank: int = 0, profile: bool = False, solver: int = 0, spmv_variant: int = 0,
                  pair_theta: float | None = None, small_path: bool = True, shard_mode: int = 0,
-                 pair_theta3: float | None = None):
+                 pair_theta3: float | None = None, peer_min_rows: int | None = None):
         self._lib = _lib.load()
         opt = Options()
         self._check(self._lib.ira_options_default(C.byref(opt)), None)
@@ -105,6 +105,8 @@ class Solver:
         opt.shard_mode = shard_mode
         if pair_theta3 is not None:
             opt.pair_theta3 = pair_theta3
+        if peer_min_rows is not None:
+            opt.peer_min_rows = peer_min_rows
         self.options = opt
         self._h = C.c_void_p()
         self._check(self._lib.ira_create(C.byref(self._h), C.byref(opt)), None)

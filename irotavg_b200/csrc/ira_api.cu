@@ -107,6 +107,7 @@ struct ira_context {
   int start_mode = 0;        // 0: resident calls restart from the uploaded Q0, 1: continue from the current Q
   int nslices = 0, npos = 0;
   int64_t sell_total = 0;
+  bool sell_built = false;   // the SELL copy exists (it may still be unused by irls: fmt_csr)
   bool fmt_csr = false;      // multi-kernel path on the CSR sub-warp kernels (lanes_per_row set)
   bool persistent = true;    // one cooperative kernel per linear solve
   bool pairing = false;      // 2x2 block-Jacobi active in the multi-kernel path
@@ -122,6 +123,7 @@ struct ira_context {
   ncclComm_t comm = nullptr;
   // peer-memory solve (ira_peer.cuh): this rank's window, the peers' windows mapped through CUDA IPC
   bool peer = false;
+  bool replicated = false;   // world_size > 1 but the graph is too small to partition: every rank solves all of it
   DevBuf peer_win, sell_pos, ipc_stage, sell_colpos;
   void* peer_mapped[kPeerMax] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void* peer_exported = nullptr;        // the window address the current mappings were exchanged for
@@ -427,7 +429,7 @@ ira_status run_pairing(ira_context* h) {
                                                      h->opt.pair_theta, h->pair_key.as<unsigned long long>(),
                                                      h->pair_w2.as<double>());
   IRA_TRY(launch_check(h, "k_pair_best"));
-  if (h->opt.world_size > 1 && !h->peer) {   // a node's edges live on several ranks: global strongest pick
+  if (h->opt.world_size > 1 && !h->peer && !h->replicated) {   // a node's edges live on several ranks: global strongest pick
     IRA_TRY(allreduce(h, h->pair_key.p, h->pair_key2.p, (size_t)h->n, ncclUint64, ncclMax));
     k_pair_select<<<grid_nodes(h, h->n), 256, 0, h->stream>>>(h->pair_key.as<unsigned long long>(),
                                                            h->pair_key2.as<unsigned long long>(), h->pair_w2.as<double>(), h->n);
@@ -442,7 +444,7 @@ ira_status run_pairing(ira_context* h) {
                                                          h->mate2.as<int>(), h->pc3.as<double>());
   IRA_TRY(launch_check(h, "k_pair_mate"));
   // third members (3x3 blocks); the edge-sharded NCCL path would need two more all-reduces per solve: pairs only
-  if (h->opt.pair_theta3 > 0.0 && (h->opt.world_size <= 1 || h->peer)) {
+  if (h->opt.pair_theta3 > 0.0 && (h->opt.world_size <= 1 || h->peer || h->replicated)) {
     IRA_CUDA(h, cudaMemsetAsync(h->att_key.p, 0, sizeof(unsigned long long) * (size_t)h->n, h->stream));
     k_attach_best<<<grid_slices(h), 256, 0, h->stream>>>(h->sell_row.as<int>(), h->slice_off.as<int>(),
                                                        h->slice_width.as<int>(), h->sell_col.as<int>(),
@@ -759,7 +761,10 @@ ira_status build_csr(ira_context* h) {
   IRA_CUDA(h, cudaMemcpyAsync(&host[0], h->rowptr.as<int>() + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   IRA_CUDA(h, cudaMemcpyAsync(&host[1], h->bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   IRA_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (host[1]) { h->err = "edge endpoint out of range [0, n_total)"; return IRA_ERR_INVALID_ARG; }
+  if (host[1] >= 2) { h->err = "edge endpoint out of range [0, n_total)"; return IRA_ERR_INVALID_ARG; }
+  // the reference's make_A turns an edge (i, i) into a single -1 entry (its second coeffRef overwrites the first,
+  // ral/l1_irls.cpp:772-776): not a relative rotation between two views - refused rather than silently reinterpreted
+  if (host[1] == 1) { h->err = "self-loop edge (i == j) is not a relative rotation between two views"; return IRA_ERR_INVALID_ARG; }
   h->nnz = host[0];
   h->lpr = pick_lpr(h);
   return IRA_OK;
@@ -919,6 +924,7 @@ ira_status ira_options_default(ira_options* o) {
   o->world_size = 1;
   o->rank = 0;
   o->profile = 0;
+  o->peer_min_rows = 120000;
   return IRA_OK;
 }
 
@@ -1002,15 +1008,21 @@ ira_status ira_problem_upload(ira_handle h, int64_t m, int64_t n_total, int32_t 
   IRA_TRY(build_csr(h));
   // SELL padding blow-up (heavy-tailed degrees) falls back to the CSR sub-warp kernels
   h->fmt_csr = h->opt.lanes_per_row >= 2;
+  h->sell_built = false;
   if (!h->fmt_csr) {
     IRA_TRY(build_sell(h));
+    h->sell_built = true;
     if (h->sell_total > 3ll * std::max(h->nnz, 1) + 64ll * kSellSigma) h->fmt_csr = true;
-    h->pcg2_ok = false;
-    if (!h->fmt_csr && h->opt.world_size <= 1) IRA_TRY(plan_pcg2(h));
   }
-  h->persistent = !h->fmt_csr && h->opt.world_size <= 1 && (h->opt.solver & 3) != 1 && h->pcg_blocks_per_sm > 0;
+  // whole graph on every rank and too small to be worth partitioning: replicated single-GPU solves
+  h->replicated = h->opt.world_size > 1 && (h->opt.shard_mode == 1 || h->opt.shard_mode == 2) &&
+                  n_total < (int64_t)h->opt.peer_min_rows && !h->fmt_csr && h->pcg_blocks_per_sm > 0;
+  const bool one_gpu = h->opt.world_size <= 1 || h->replicated;
+  h->pcg2_ok = false;
+  if (!h->fmt_csr && one_gpu) IRA_TRY(plan_pcg2(h));
+  h->persistent = !h->fmt_csr && one_gpu && ((h->opt.solver & 3) != 1 || h->replicated) && h->pcg_blocks_per_sm > 0;
   h->peer = false;
-  if ((h->opt.world_size > 1 && (h->opt.shard_mode == 1 || h->opt.shard_mode == 2)) ||
+  if ((h->opt.world_size > 1 && !h->replicated && (h->opt.shard_mode == 1 || h->opt.shard_mode == 2)) ||
       (h->opt.world_size <= 1 && (h->opt.solver & 8))) {
     if (h->fmt_csr || h->pcg_blocks_per_sm <= 0) { h->err = "peer-memory solve needs the SELL pattern and cooperative launch"; return IRA_ERR_INVALID_ARG; }
     IRA_TRY(peer_setup(h));
@@ -1475,9 +1487,14 @@ ira_status ira_l1ra_resident(ira_handle h, int32_t max_iters, double change_th, 
                              double* runtime_s_out, ira_stats* stats) {
   if (!h) return IRA_ERR_INVALID_ARG;
   if (!h->uploaded) return IRA_ERR_NOT_UPLOADED;
-  if (h->opt.world_size > 1) { h->err = "l1ra is single-GPU in this version"; return IRA_ERR_INVALID_ARG; }
-  if (h->fmt_csr || h->pcg_blocks_per_sm <= 0) { h->err = "l1ra needs the SELL pattern and cooperative launch"; return IRA_ERR_INVALID_ARG; }
+  // world_size > 1: with the whole graph on every rank (shard_mode 1 / 2) each rank runs the stage itself - the
+  // results are bitwise identical on all ranks (deterministic kernels); edge shards (shard_mode 0) cannot
+  if (h->opt.world_size > 1 && !h->peer && !h->replicated) { h->err = "l1ra with world_size > 1 needs the whole graph on every rank (shard_mode 1)"; return IRA_ERR_INVALID_ARG; }
+  if (h->pcg_blocks_per_sm <= 0) { h->err = "l1ra needs cooperative launch"; return IRA_ERR_INVALID_ARG; }
   IRA_CUDA(h, cudaSetDevice(h->device));
+  // irls may have chosen the CSR kernels (lanes_per_row set, or SELL padding blow-up on hub graphs); l1ra's
+  // kernels walk the SELL copy whatever its padding: build it now if the upload did not
+  if (!h->sell_built) { IRA_TRY(build_sell(h)); h->sell_built = true; }
   const auto t0 = std::chrono::steady_clock::now();
   const int launches0 = h->launches;
   if (stats) memset(stats, 0, sizeof *stats);
@@ -1652,6 +1669,8 @@ ira_status small_l1ra_irls(ira_context* h, int m, int n, int f, const int32_t* I
   }
   for (int k = 0; k < 2 * m; ++k)
     if (I_pairs[k] < 0 || I_pairs[k] >= n) { h->err = "edge endpoint out of range [0, n_total)"; return IRA_ERR_INVALID_ARG; }
+  for (int k = 0; k < m; ++k)
+    if (I_pairs[2 * k] == I_pairs[2 * k + 1]) { h->err = "self-loop edge (i == j) is not a relative rotation between two views"; return IRA_ERR_INVALID_ARG; }
   SmallIn hd;
   memset(&hd, 0, sizeof hd);
   hd.m = m; hd.n = n; hd.f = f; hd.cost = cost; hd.l1_max_iters = l1_max; hd.irls_max_iters = irls_max;

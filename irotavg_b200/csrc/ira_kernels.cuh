@@ -190,7 +190,8 @@ __global__ void k_csr_keys(const int2* __restrict__ I, int64_t m, int n, int f, 
                            int* __restrict__ vals, int* __restrict__ bad) {
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < m; k += (int64_t)gridDim.x * blockDim.x) {
     const int2 e = I[k];
-    if (e.x < 0 || e.x >= n || e.y < 0 || e.y >= n) { atomicExch(bad, 1); keys[2 * k] = n; keys[2 * k + 1] = n; }
+    if (e.x < 0 || e.x >= n || e.y < 0 || e.y >= n) { atomicMax(bad, 2); keys[2 * k] = n; keys[2 * k + 1] = n; }
+    else if (e.x == e.y) { atomicMax(bad, 1); keys[2 * k] = n; keys[2 * k + 1] = n; }   // self-loop: rejected by the host
     else {
       keys[2 * k] = e.y >= f ? e.y : n;
       keys[2 * k + 1] = e.x >= f ? e.x : n;

@@ -71,3 +71,26 @@ def test_l1ra_zero_iterations_and_errors(solver):
     assert info.iters == 0 and np.array_equal(Q, g.Q0)
     with pytest.raises(ira.IraError):
         solver.l1ra(g.QQ, g.I, None, g.Q0, 0, 3, 1e-3)
+
+
+def test_l1ra_on_a_hub_graph(built_lib):
+    """A star-like view graph (one hub tied to every node): the SELL padding blow-up makes irls fall back to its
+    CSR kernels; l1ra must still run (it used to return IRA_ERR_INVALID_ARG) and match the oracle."""
+    import irotavg_b200 as ira
+    rng = np.random.default_rng(9)
+    n = 6000
+    base = G.small_graph(n=n, extra=1500, sigma_n=0.01, sigma_init=0.05, seed=9)
+    hub = np.stack([np.full(n - 2, 1), np.arange(2, n)], axis=1).astype(np.int32)       # node 1 sees everybody
+    I = np.concatenate([base.I, hub])
+    Qgt = base.Qgt
+    QQh = O.quat_mult(Qgt[hub[:, 1]], Qgt[hub[:, 0]] * np.array([-1.0, -1.0, -1.0, 1.0]))
+    QQ = np.concatenate([base.QQ, QQh])
+    for lanes in (0, 8):                                                                # 8: irls on the CSR kernels by request
+        with ira.Solver(lanes_per_row=lanes) as s:
+            Q, info = s.l1ra(QQ, I, None, base.Q0, base.f, 3, 1e-6)
+            Q2, w2, info2 = s.irls(QQ, I, None, O.GEMAN_MCCLURE, SIGMA, Q, base.f, 5, -1.0)
+        ref = O.l1ra(QQ, I, None, base.Q0, base.f, 3, 1e-6)
+        assert info.iters == ref.iters
+        assert O.geodesic_rms(Q, ref.Q, base.f) <= 1e-8
+        ref2 = O.irls(QQ, I, None, O.GEMAN_MCCLURE, SIGMA, ref.Q, base.f, 5, -1.0, solver="direct")
+        assert O.geodesic_rms(Q2, ref2.Q, base.f) <= 1e-8

@@ -55,7 +55,8 @@ PEER_WORKER = textwrap.dedent("""
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     sigma = 5 * np.pi / 180
-    s = ira.Solver(device=lr, world_size=world, rank=rank, shard_mode=int(os.environ["IRA_SHARD_MODE"]))
+    s = ira.Solver(device=lr, world_size=world, rank=rank, shard_mode=int(os.environ["IRA_SHARD_MODE"]),
+                   peer_min_rows=int(os.environ.get("IRA_PEER_MIN_ROWS", "0")))   # 0: partition even these small graphs
     s.comm_init(broadcast_unique_id(dist, ira.Solver, rank, device="cuda"))
     ref = np.load(os.environ["IRA_REF"])                # oracle results computed once by the parent process
     ok = True
@@ -116,6 +117,29 @@ def test_peer_memory_solve(tmp_path, built_lib, shard_mode):
     res = _torchrun(tmp_path, PEER_WORKER, min(nd, 8) if nd in (2, 4, 8) else 2,
                     extra_env={"IRA_REF": str(tmp_path / "ref.npz"), "IRA_GRAPHS": repr(PEER_GRAPHS),
                                "IRA_SHARD_MODE": str(shard_mode)})
+    print(res.stdout[-3000:])
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_small_graph_dispatch_replicated(tmp_path, built_lib):
+    """Default peer_min_rows: graphs this small are not partitioned - every rank solves the whole problem with the
+    single-GPU kernels; same oracle parity, bitwise identical on all ranks, no exchange."""
+    import irotavg_b200 as ira
+    import numpy as np
+    from oracle import graphs as G, irls_oracle as O
+    nd = ira.device_count()
+    if nd < 2:
+        pytest.skip("needs 2 GPUs")
+    sigma = 5 * np.pi / 180
+    ref = {}
+    for gi, kw in enumerate(PEER_GRAPHS[:1]):
+        g = G.small_graph(**kw)
+        for cost, its in ((O.L1, 14), (O.GEMAN_MCCLURE, 6)):
+            r = O.irls(g.QQ, g.I, None, cost, sigma, g.Q0, g.f, its, -1.0, solver="direct")
+            ref[f"Q_{gi}_{cost}"], ref[f"w_{gi}_{cost}"] = r.Q, r.weights
+    np.savez(tmp_path / "ref.npz", **ref)
+    res = _torchrun(tmp_path, PEER_WORKER, 2, extra_env={"IRA_REF": str(tmp_path / "ref.npz"), "IRA_GRAPHS": repr(PEER_GRAPHS[:1]),
+                                                        "IRA_SHARD_MODE": "1", "IRA_PEER_MIN_ROWS": "120000"})
     print(res.stdout[-3000:])
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
 

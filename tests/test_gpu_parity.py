@@ -236,6 +236,19 @@ def test_empty_and_degenerate_inputs(solver):
     bad[3, 1] = g.n
     with pytest.raises(ira.IraError):
         solver.irls(g.QQ, bad, None, O.L1, SIGMA, g.Q0, g.f, 3, -1.0)
+    # a self-loop (i == j) is refused (the reference's make_A would silently turn it into a single -1 entry),
+    # by the general pipeline and by the single-block window solver alike
+    loop = g.I.copy()
+    loop[5] = [7, 7]
+    with pytest.raises(ira.IraError) as e:
+        solver.irls(g.QQ, loop, None, O.L1, SIGMA, g.Q0, g.f, 3, -1.0)
+    assert e.value.status == 1 and "self-loop" in str(e.value)
+    gw = G.small_graph(n=15, extra=27, sigma_n=0.005, sigma_init=0.05, seed=1, f=4)
+    loopw = gw.I.copy()
+    loopw[2] = [9, 9]
+    with pytest.raises(ira.IraError) as e:
+        solver.l1ra_irls(gw.QQ, loopw, gw.Q0, gw.f, 10, 1e-3, O.GEMAN_MCCLURE, SIGMA, 10, 1e-3)
+    assert "self-loop" in str(e.value)
     # the handle is still usable afterwards
     Q, w, info = solver.irls(g.QQ, g.I, None, O.L2, SIGMA, g.Q0, g.f, 3, -1.0)
     assert O.geodesic_rms(Q, ref.Q, g.f) <= RMS_TOL
@@ -252,11 +265,12 @@ def test_large_angle_identity_start(solver):
     assert O.geodesic_rms(Q, ref.Q, g.f) <= RMS_TOL
 
 
-@pytest.mark.parametrize("solver_kind", [1, 2, 6, 8, 12])
+@pytest.mark.parametrize("solver_kind", [1, 2, 6, 8, 12, 16])
 @pytest.mark.parametrize("maker", ["random", "kitti", "tiny"])
 def test_solver_variants(built_lib, solver_kind, maker):
     """solver 1 = one kernel per CG step (SELL SpMV, host-polled), 2 = persistent cooperative PCG
-    (register-resident state when one row per lane fits), 6 = persistent with HBM-resident vectors, 8 / 12 = the
+    (register-resident state when one row per lane fits; the matrix in shared memory, ira_pcg2.cuh, unless 16 is
+    added), 6 = persistent with HBM-resident vectors, 8 / 12 = the
     barrier-free kernels of the multi-GPU path (self-validating data, ira_peer.cuh) on ONE GPU, register- /
     HBM-resident."""
     import irotavg_b200 as ira
