@@ -192,14 +192,15 @@ ira_status ira_l1ra_irls(ira_handle h, int64_t m, int64_t n_total, int32_t f,
 /* ---- irotavg::init_mst  (ral/l1_irls.hpp:89-90, ral/l1_irls.cpp:915-979) ----------------------
  * Spanning-tree start: the reference sweeps the edge list in order until every node is flagged; the
  * tree (and so the result) depends on the edge order.  The device reproduces exactly that tree
- * (time-stamp relaxation, irotavg_b200/csrc/ira_mst.cuh) and the same one product per node.  Rows
+ * (time-stamp relaxation, irotavg_b200/csrc/ira_mst.cuh) and the same chain of products per node, associated by
+ * pointer jumping (O(log depth) rounds; differences to the sequential evaluation are rounding only).  Rows
  * [0, f_init) of Q are kept (ral/test.cpp:285-286 passes max(#given rotations, f)); the others are
  * overwritten.  IRA_ERR_NOT_SPANNING when the edges do not reach every node (:970-977; Q undefined).
  * The resident form acts on the uploaded problem: both the restart copy Q0 and the current Q get the
  * tree start, so that ira_l1ra_resident / ira_irls_resident follow without crossing PCIe. */
 typedef struct ira_mst_stats {
   int32_t passes_label;       /* relaxation passes until the time stamps were final          */
-  int32_t passes_propagate;   /* passes of the rotation propagation                          */
+  int32_t passes_propagate;   /* pointer-jumping rounds of the rotation propagation          */
   int32_t unreached;          /* nodes not spanned                                           */
   double  t_ms;               /* device time (CUDA events)                                   */
 } ira_mst_stats;

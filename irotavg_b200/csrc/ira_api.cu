@@ -100,7 +100,7 @@ struct ira_context {
   DevBuf pdU, pdAX, pdL1, pdL2, pdADX, pdDU, pdDL1, pdDL2, pdEV, pdSIGX, sell_w3;
   DevBuf pdX, pdATV, pdATDV, pdW1P, pdDX, diag3, dinv3, pdctl, pdtrial;
   PdCtl* h_pdctl = nullptr;  // pinned
-  DevBuf mst_label, mst_label2, mst_order, mst_order2, mst_done, mst_ctl;   // init_mst (ira_mst.cuh)
+  DevBuf mst_label, mst_label2, mst_order, mst_order2, mst_done, mst_ctl, mst_T0, mst_T1;   // init_mst (ira_mst.cuh)
   unsigned char* small_in = nullptr;    // mapped pinned blocks of the single-block window solver (ira_small.cuh)
   unsigned char* small_out = nullptr;
   bool small_ready = false;
@@ -976,7 +976,7 @@ ira_status ira_destroy(ira_handle h) {
                     &h->R2, &h->S2, &h->pdU, &h->pdAX, &h->pdL1, &h->pdL2, &h->pdADX, &h->pdDU, &h->pdDL1, &h->pdDL2, &h->pdEV,
                     &h->pdSIGX, &h->sell_w3, &h->pdX, &h->pdATV, &h->pdATDV, &h->pdW1P, &h->pdDX, &h->diag3, &h->dinv3,
                     &h->pdctl, &h->pdtrial, &h->mst_label, &h->mst_label2, &h->mst_order, &h->mst_order2, &h->mst_done,
-                    &h->mst_ctl, &h->sell_pos, &h->ipc_stage, &h->sell_colpos, &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs, &h->mate2, &h->pc3, &h->att_key})
+                    &h->mst_ctl, &h->mst_T0, &h->mst_T1, &h->sell_pos, &h->ipc_stage, &h->sell_colpos, &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs, &h->mate2, &h->pc3, &h->att_key})
     b->release();
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -1569,6 +1569,8 @@ ira_status ira_init_mst_resident(ira_handle h, int32_t f_init, ira_mst_stats* st
   IRA_CUDA(h, h->mst_order.reserve(sizeof(int) * (size_t)n));
   IRA_CUDA(h, h->mst_order2.reserve(sizeof(int) * (size_t)n));
   IRA_CUDA(h, h->mst_done.reserve(sizeof(int) * (size_t)n));
+  IRA_CUDA(h, h->mst_T0.reserve(sizeof(double4) * (size_t)n));
+  IRA_CUDA(h, h->mst_T1.reserve(sizeof(double4) * (size_t)n));
   IRA_CUDA(h, h->mst_ctl.reserve(sizeof(MstCtl)));
   EventPair evp;
   IRA_CUDA(h, evp.create());
@@ -1585,38 +1587,28 @@ ira_status ira_init_mst_resident(ira_handle h, int32_t f_init, ira_mst_stats* st
     int64_t mm = m;
     unsigned long long* lab = h->mst_label.as<unsigned long long>();
     MstCtl* ctl = h->mst_ctl.as<MstCtl>();
-    const int grid = std::max(1, std::min(cdiv(cdiv(std::max<int64_t>(m, 1), kMstEdgeChunk), 256), h->sms * per_sm));
+    // one warp per segment of kMstSeg consecutive edges
+    const int grid = std::max(1, std::min(cdiv(cdiv(std::max<int64_t>(m, 1), kMstSeg) * 32, 256), h->sms * per_sm));
     void* args[] = {(void*)&I, (void*)&mm, (void*)&lab, (void*)&ctl};
     IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_mst_labels, dim3(grid), dim3(256), args, 0, h->stream));
     h->launches++;
   }
-  {                                                                       // nodes in the order the sweeps flag them
-    size_t tmp_bytes = 0;
-    IRA_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->mst_label.as<unsigned long long>(),
-                                                h->mst_label2.as<unsigned long long>(), h->mst_order.as<int>(),
-                                                h->mst_order2.as<int>(), n, 0, 64, h->stream));
-    IRA_CUDA(h, h->cubtmp.reserve(tmp_bytes));
-    IRA_CUDA(h, cub::DeviceRadixSort::SortPairs(h->cubtmp.p, tmp_bytes, h->mst_label.as<unsigned long long>(),
-                                                h->mst_label2.as<unsigned long long>(), h->mst_order.as<int>(),
-                                                h->mst_order2.as<int>(), n, 0, 64, h->stream));
-    h->launches += 8;
-  }
-  IRA_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mst_propagate, 256, 0));
+  // parents and factors from the labels, then the tree contracted by pointer jumping (O(log depth) rounds)
+  k_mst_parents<<<grid_nodes(h, n), 256, 0, h->stream>>>(h->I.as<int2>(), h->QQ.as<double>(), h->m_pad,
+                                                       h->mst_label.as<unsigned long long>(), n, f_init,
+                                                       h->mst_order.as<int>(), h->mst_T0.as<double4>(), h->mst_ctl.as<MstCtl>());
+  IRA_TRY(launch_check(h, "k_mst_parents"));
+  IRA_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mst_jump, 256, 0));
   per_sm = std::max(1, std::min(per_sm, 4));
   {
-    const int2* I = h->I.as<int2>();
-    const double* QQ = h->QQ.as<double>();
-    int64_t ld = h->m_pad;
-    const int* order = h->mst_order2.as<int>();
-    const unsigned long long* lab = h->mst_label.as<unsigned long long>();
-    int nn = n, fi = f_init;
+    int* a0 = h->mst_order.as<int>(); int* a1 = h->mst_order2.as<int>();
+    double4* t0 = h->mst_T0.as<double4>(); double4* t1 = h->mst_T1.as<double4>();
+    int nn = n;
     double4* Q = h->Q0.as<double4>();
-    int* done = h->mst_done.as<int>();
     MstCtl* ctl = h->mst_ctl.as<MstCtl>();
-    const int grid = std::max(1, std::min(cdiv(cdiv(n, kMstNodeChunk), 256), h->sms * per_sm));
-    void* args[] = {(void*)&I, (void*)&QQ, (void*)&ld, (void*)&order, (void*)&lab, (void*)&nn, (void*)&fi,
-                    (void*)&Q, (void*)&done, (void*)&ctl};
-    IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_mst_propagate, dim3(grid), dim3(256), args, 0, h->stream));
+    const int grid = std::max(1, std::min(cdiv(n, 256), h->sms * per_sm));
+    void* args[] = {(void*)&a0, (void*)&t0, (void*)&a1, (void*)&t1, (void*)&nn, (void*)&Q, (void*)&ctl};
+    IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_mst_jump, dim3(grid), dim3(256), args, 0, h->stream));
     h->launches++;
   }
   IRA_CUDA(h, cudaMemcpyAsync(h->Q.p, h->Q0.p, sizeof(double4) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));

@@ -11,15 +11,23 @@
 // sweep when u was flagged by an earlier edge of the list, the next sweep otherwise.  label(v) is the
 // minimum of that over v's edges - a monotone shortest-path problem, solved by label-correcting
 // relaxation (atomicMin) to its fixed point, which is unique and equals the sequential result.
-// Each thread relaxes a chunk of consecutive edges in list order, so a chain laid out in edge order
-// advances a whole chunk per pass instead of one hop.
+// Chains laid out in edge order are the practical case (a SLAM sequence; the synthetic configs list their path
+// first: ONE sweep flags 100 000 nodes one after the other), so the relaxation is organised for them: every warp
+// owns a SEGMENT of kMstSeg consecutive edges per pass and walks it in groups of 32; the 32 edges' endpoint labels
+// are loaded at once and the group is relaxed to its local fixed point IN REGISTERS (the lowest lane that can
+// still improve a label applies its update, every lane patches its own copy by shuffle) - a hop costs ~50 cycles
+// instead of an L2 round trip, and a chain advances a whole segment per pass (config 3: 25 passes, ~3 ms; the
+// first version needed 3 126 passes of 30 us).
 //
 // With the labels final, node v's parent edge is (label & 0xffffffff) - 1 and
 //     Q_v = QQ_k (x) Q_u          when v is the edge's second endpoint (:941)
 //     Q_v = [QQ_k.xyz, -QQ_k.w] (x) Q_u   when v is the first (:955-958, the reference's sign)
-// each computed once from the parent's final value, exactly as in the reference (rows < f_init keep
-// their value, :939,953, but still propagate).  Nodes are visited in label order (radix sort), a chunk
-// of consecutive positions per thread, in passes until no node waits for its parent.
+// (rows < f_init keep their value, :939,953, but still propagate).  The reference evaluates these products one
+// after the other down the tree - 100 000 dependent products on config 3.  Here the tree is contracted by POINTER
+// JUMPING: every node holds (ancestor a, T) with Q_v = T (x) Q_a; a round replaces (a, T) by (a's ancestor,
+// T (x) T_a); after ceil(log2(depth)) rounds every ancestor is a root (node 0, a given rotation, or an unreached
+// node) and one product finishes the node.  Same parents, same factors, a different association of the same
+// product: differences are rounding only (<= 1e-13 on the 100 000-hop chain of config 3, tested).
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -30,8 +38,6 @@
 namespace ira {
 namespace cg = cooperative_groups;
 
-constexpr int kMstEdgeChunk = 32;
-constexpr int kMstNodeChunk = 16;
 constexpr unsigned long long kMstInf = ~0ull;
 
 struct MstCtl {
@@ -65,83 +71,137 @@ __device__ __forceinline__ unsigned long long mst_next(unsigned long long t, uns
   return (sweep << 32) | k1;
 }
 
-__global__ void __launch_bounds__(256)
-k_mst_labels(const int2* __restrict__ I, int64_t m, unsigned long long* label, MstCtl* ctl) {
-  cg::grid_group grid = cg::this_grid();
-  const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  const int64_t nchunks = (m + kMstEdgeChunk - 1) / kMstEdgeChunk;
-  int pass = 0;
-  for (;; ++pass) {
-    const int slot = pass % 3;
-    if (gtid == 0) ctl->changed[(pass + 1) % 3] = 0;
-    bool moved = false;
-    for (int64_t c = gtid; c < nchunks; c += nthreads) {
-      const int64_t k0 = c * kMstEdgeChunk, k1 = min(m, k0 + (int64_t)kMstEdgeChunk);
-      for (int64_t k = k0; k < k1; ++k) {
-        const int2 e = __ldg(I + k);
-        if (e.x == e.y) continue;
-        const unsigned long long tu = __ldcg(label + e.x);
-        unsigned long long tv = __ldcg(label + e.y);
-        if (tu != kMstInf) {                                  // flags[e1] && !flags[e2]  (:934)
-          const unsigned long long cand = mst_next(tu, (unsigned long long)k + 1ull);
-          if (cand < tv) { atomicMin(label + e.y, cand); tv = cand; moved = true; }
-        }
-        if (tv != kMstInf) {                                  // !flags[e1] && flags[e2]  (:950)
-          const unsigned long long cand = mst_next(tv, (unsigned long long)k + 1ull);
-          if (cand < tu) { atomicMin(label + e.x, cand); moved = true; }
-        }
-      }
-    }
-    if (__any_sync(0xffffffffu, moved) && (threadIdx.x & 31) == 0) atomicOr(&ctl->changed[slot], 1);
-    grid.sync();
-    if (!__ldcg(&ctl->changed[slot])) break;
-  }
-  if (gtid == 0) ctl->passes_label = pass + 1;
+constexpr int kMstSeg = 4096;          // consecutive edges one warp relaxes per pass (multiple of 32)
+
+// can edge (tu, tv) with 1-based index k1 still improve one of its endpoint labels?
+__device__ __forceinline__ bool mst_can(unsigned long long tu, unsigned long long tv, unsigned long long k1) {
+  return (tu != kMstInf && mst_next(tu, k1) < tv) || (tv != kMstInf && mst_next(tv, k1) < tu);
 }
 
 __global__ void __launch_bounds__(256)
-k_mst_propagate(const int2* __restrict__ I, const double* __restrict__ QQ, int64_t ldqq,
-                const int* __restrict__ order, const unsigned long long* __restrict__ label, int n, int f_init,
-                double4* Q, int* done, MstCtl* ctl) {
+k_mst_labels(const int2* __restrict__ I, int64_t m, unsigned long long* label, MstCtl* ctl) {
   cg::grid_group grid = cg::this_grid();
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nthreads = gridDim.x * blockDim.x;
-  const int nchunks = (n + kMstNodeChunk - 1) / kMstNodeChunk;
-  int unreached = 0;
+  const int lane = threadIdx.x & 31;
+  const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t nseg = (m + kMstSeg - 1) / kMstSeg;
   int pass = 0;
   for (;; ++pass) {
     const int slot = pass % 3;
-    if (gtid == 0) ctl->changed[(pass + 1) % 3] = 0;
-    bool waiting = false;
-    for (int c = gtid; c < nchunks; c += nthreads) {
-      const int p0 = c * kMstNodeChunk, p1 = min(n, p0 + kMstNodeChunk);
-      for (int pos = p0; pos < p1; ++pos) {
-        const int v = order[pos];
-        if (__ldcg(done + v)) continue;
-        const unsigned long long lab = label[v];
-        if (lab == kMstInf) { if (pass == 0) ++unreached; continue; }
-        const int64_t k = (int64_t)(lab & 0xffffffffull) - 1;
-        const int2 e = __ldg(I + k);
-        const int u = e.x == v ? e.y : e.x;
-        if (!__ldcg(done + u)) { waiting = true; continue; }
-        if (v >= f_init) {                                   // do not change known rotations (:939,953)
-          __threadfence();                                   // the parent's Q was published before its flag
-          const double4 qu = ldcg256(Q + u);
-          double4 qq = make_double4(QQ[k], QQ[ldqq + k], QQ[2 * ldqq + k], QQ[3 * ldqq + k]);
-          if (e.x == v) qq.w = -qq.w;                        // QQj_inv(3) *= -1  (:956-957)
-          st256(Q + v, quat_mult(qq, qu));
-          __threadfence();
+    if (gwarp == 0 && lane == 0) ctl->changed[(pass + 1) % 3] = 0;
+    bool moved = false;
+    for (int64_t sg = gwarp; sg < nseg; sg += nwarps) {
+      const int64_t s0 = sg * kMstSeg, s1 = min(m, s0 + (int64_t)kMstSeg);
+      for (int64_t k0 = s0; k0 < s1; k0 += 32) {
+        const int64_t k = k0 + lane;
+        int2 e = make_int2(0, 0);
+        unsigned long long tu = kMstInf, tv = kMstInf;
+        if (k < s1) {
+          e = __ldg(I + k);
+          if (e.x != e.y) { tu = __ldcg(label + e.x); tv = __ldcg(label + e.y); }
         }
-        atomicExch(done + v, 1);
+        const unsigned long long k1 = (unsigned long long)k + 1ull;
+        // relax the group to its local fixed point: the lowest lane that can improve a label goes first
+        unsigned int can = __ballot_sync(0xffffffffu, mst_can(tu, tv, k1));
+        while (can) {
+          const int j = __ffs(can) - 1;
+          const int ex = __shfl_sync(0xffffffffu, e.x, j), ey = __shfl_sync(0xffffffffu, e.y, j);
+          unsigned long long tuj = __shfl_sync(0xffffffffu, tu, j), tvj = __shfl_sync(0xffffffffu, tv, j);
+          const unsigned long long kj = (unsigned long long)(k0 + j) + 1ull;
+          if (tuj != kMstInf) {                                 // flags[e1] && !flags[e2]  (:934)
+            const unsigned long long cand = mst_next(tuj, kj);
+            if (cand < tvj) {
+              tvj = cand;
+              if (lane == j) atomicMin(label + ey, cand);
+              if (e.x == ey && cand < tu) tu = cand;
+              if (e.y == ey && cand < tv) tv = cand;
+            }
+          }
+          if (tvj != kMstInf) {                                 // !flags[e1] && flags[e2]  (:950)
+            const unsigned long long cand = mst_next(tvj, kj);
+            if (cand < tuj) {
+              if (lane == j) atomicMin(label + ex, cand);
+              if (e.x == ex && cand < tu) tu = cand;
+              if (e.y == ex && cand < tv) tv = cand;
+            }
+          }
+          moved = true;
+          can = __ballot_sync(0xffffffffu, mst_can(tu, tv, k1));
+        }
       }
     }
-    if (__any_sync(0xffffffffu, waiting) && (threadIdx.x & 31) == 0) atomicOr(&ctl->changed[slot], 1);
+    if (moved && lane == 0) atomicOr(&ctl->changed[slot], 1);
     grid.sync();
     if (!__ldcg(&ctl->changed[slot])) break;
   }
+  if (gwarp == 0 && lane == 0) ctl->passes_label = pass + 1;
+}
+
+// Parent and factor of every node from its final label: roots (node 0, given rotations, unreached nodes) point to
+// themselves with the identity.
+__global__ void __launch_bounds__(256)
+k_mst_parents(const int2* __restrict__ I, const double* __restrict__ QQ, int64_t ldqq,
+              const unsigned long long* __restrict__ label, int n, int f_init, int* __restrict__ anc,
+              double4* __restrict__ T, MstCtl* ctl) {
+  int unreached = 0;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+    const unsigned long long lab = label[v];
+    int a = v;
+    double4 t = make_double4(0.0, 0.0, 0.0, 1.0);
+    if (lab == kMstInf) ++unreached;
+    else if (v >= f_init && lab != 0ull) {                   // do not change known rotations (:939,953)
+      const int64_t k = (int64_t)(lab & 0xffffffffull) - 1;
+      const int2 e = __ldg(I + k);
+      a = e.x == v ? e.y : e.x;
+      t = make_double4(QQ[k], QQ[ldqq + k], QQ[2 * ldqq + k], QQ[3 * ldqq + k]);
+      if (e.x == v) t.w = -t.w;                              // QQj_inv(3) *= -1  (:956-957)
+    }
+    anc[v] = a;
+    st256(T + v, t);
+  }
   if (unreached) atomicAdd(&ctl->unreached, unreached);
-  if (gtid == 0) ctl->passes_prop = pass + 1;
+}
+
+// Pointer jumping, double-buffered: (anc, T) <- (anc[anc], T (x) T[anc]) until every ancestor is a root, then
+// Q_v = T_v (x) Q_root.  Roots are the nodes with anc == self; they are never written.
+__global__ void __launch_bounds__(256)
+k_mst_jump(int* anc0, double4* T0, int* anc1, double4* T1, int n, double4* Q, MstCtl* ctl) {
+  cg::grid_group grid = cg::this_grid();
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nthreads = gridDim.x * blockDim.x;
+  int* a_in = anc0; int* a_out = anc1;
+  double4* t_in = T0; double4* t_out = T1;
+  int round = 0;
+  for (;; ++round) {
+    const int slot = round % 3;
+    if (gtid == 0) ctl->changed[(round + 1) % 3] = 0;
+    bool again = false;
+    for (int v = gtid; v < n; v += nthreads) {
+      const int a = __ldcg(a_in + v);
+      double4 t = ldcg256(t_in + v);
+      int a2 = a;
+      if (a != v) {
+        const int aa = __ldcg(a_in + a);
+        if (aa != a) {                                       // the ancestor is not a root yet: jump over it
+          t = quat_mult(t, ldcg256(t_in + a));
+          a2 = aa;
+          if (__ldcg(a_in + aa) != aa) again = true;
+        }
+      }
+      a_out[v] = a2;
+      st256(t_out + v, t);
+    }
+    if (__any_sync(0xffffffffu, again) && (threadIdx.x & 31) == 0) atomicOr(&ctl->changed[slot], 1);
+    grid.sync();
+    int* ta = a_in; a_in = a_out; a_out = ta;
+    double4* tt = t_in; t_in = t_out; t_out = tt;
+    if (!__ldcg(&ctl->changed[slot])) break;
+  }
+  for (int v = gtid; v < n; v += nthreads) {
+    const int a = __ldcg(a_in + v);
+    if (a != v) st256(Q + v, quat_mult(ldcg256(t_in + v), ldcg256(Q + a)));
+  }
+  if (gtid == 0) ctl->passes_prop = round + 1;
 }
 
 }  // namespace ira
