@@ -1,9 +1,12 @@
 // Replays an op list (oracle/rotavg_stream.py:write_ops) through the REFERENCE'S OWN ViewGraph::rotAvg source
 // (compiled from the text tools/make_dropin.py extracts out of /root/reference/src/ViewGraph.cpp) on top of the
 // adapter header irotavg_b200/host/l1_irls.hpp + libira.so: the literal drop-in.  Output: like rotavg_main.cpp
-// (every view's rotation, row-major, 17 digits), then one line per call with the window size, then the
+// (every view's rotation, row-major, 17 digits), then one line per call "window-size wall-seconds", then the
 // reference's savePoses() text for the same views.
 //   rotavg_refsrc ops.txt out.txt poses.txt
+// The same file linked against oracle/_ref (the reference's ral/l1_irls.cpp itself, oracle/build_ref.py) instead of
+// the adapter + libira.so is `oracle/_ref/rotavg_reference`: the reference's complete CPU path for config 5.
+#include <chrono>
 #include <cstdio>
 #include <string>
 
@@ -19,6 +22,7 @@ int main(int argc, char** argv) {
   in >> nops;
   ViewGraph vg;
   std::vector<int> calls;
+  std::vector<double> secs;
   for (long k = 0; k < nops; ++k) {
     std::string op;
     in >> op;
@@ -39,7 +43,9 @@ int main(int argc, char** argv) {
     } else if (op == "A") {
       int win = 0;
       in >> win;
+      const auto t0 = std::chrono::steady_clock::now();
       vg.rotAvg(win);
+      secs.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
       calls.push_back(win);
     } else {
       std::fprintf(stderr, "bad op '%s'\n", op.c_str());
@@ -54,7 +60,7 @@ int main(int argc, char** argv) {
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c) out << R(r, c) << (r == 2 && c == 2 ? "\n" : " ");
   }
-  for (size_t k = 0; k < calls.size(); ++k) out << calls[k] << "\n";
+  for (size_t k = 0; k < calls.size(); ++k) out << calls[k] << " " << secs[k] << "\n";
   out.close();
   vg.savePoses(argv[3]);
   return 0;

@@ -82,6 +82,33 @@ def test_oracle_rotavg_recovers_a_noise_free_stream():
     assert all(r["solved"] for r in reps[2:])
 
 
+@pytest.mark.parametrize("variant", ["loops", "fixes"])
+def test_oracle_stream_vs_reference_build(tmp_path, variant):
+    """Pins oracle/rotavg_stream.py to the reference's OWN rotAvg: oracle/_ref/rotavg_reference is the source text of
+    ViewGraph::rotAvg / rmat2quat / fixPose (src/ViewGraph.cpp:1175-1435) compiled with the reference's ral/l1_irls.cpp
+    (oracle/build_ref.py); same op list, same rotations (std::map pointer order vs sorted order: rounding only)."""
+    from oracle import build_ref
+    try:
+        build_ref.build()
+    except RuntimeError:
+        pytest.skip("oracle/_ref not available here")
+    if variant == "loops":
+        ops, _ = RS.make_stream(n_frames=120, loop_every=40, min_loop_gap=20)
+    else:
+        ops, _ = RS.make_stream(n_frames=90, loop_every=0, fix_every=7, seed=5)
+    inp, outp = str(tmp_path / "ops.txt"), str(tmp_path / "out.txt")
+    RS.write_ops(inp, ops)
+    subprocess.run([build_ref.ROTAVG, inp, outp, str(tmp_path / "poses.txt")], check=True, stdout=subprocess.DEVNULL,
+                   env=dict(os.environ, OMP_NUM_THREADS="1"))     # tiny dense solves: OpenMP teams only add overhead
+    tok = open(outp).read().split()
+    nv = int(tok[0])
+    R = np.array(tok[2:2 + 9 * nv], dtype=np.float64).reshape(nv, 3, 3)
+    Rref, reps = RS.replay(ops)
+    Q = np.array([O.rmat2quat(r) for r in R])
+    Qr = np.array([O.rmat2quat(r) for r in Rref])
+    assert O.geodesic_rms(Q, Qr, 0) <= 1e-11
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("variant", ["loops", "fixes"])
 def test_stream_matches_oracle(tmp_path, built_lib, variant):

@@ -65,6 +65,37 @@ def run(frames=10000, loop_every=500, cpu_frames=150):
             "unit": "calls/s", "frames": args.frames, "loop_every": args.loop_every, "wall_s_incl_parsing": wall,
             "local": stats(~glob), "global": stats(glob),
             "geodesic_rms_vs_ground_truth_rad": float(O.geodesic_rms(Q, Qgt, 1))}
+    # the reference's own CPU path on the same stream: oracle/_ref/rotavg_reference = the source text of
+    # ViewGraph::rotAvg + ral/l1_irls.cpp compiled by oracle/build_ref.py (dense stand-in solvers: window-sized problems
+    # only, so the prefix before the first global call)
+    try:
+        from oracle import build_ref
+        if build_ref.built():
+            sub = []
+            for op in ops:
+                if op[0] == "A" and op[1] > 1000:
+                    break
+                sub.append(op)
+            inp2, out2 = os.path.join(tmp, "ops_ref.txt"), os.path.join(tmp, "out_ref.txt")
+            RS.write_ops(inp2, sub)
+            env = dict(os.environ, OMP_NUM_THREADS="1")
+            subprocess.run([build_ref.ROTAVG, inp2, out2, os.path.join(tmp, "poses_ref.txt")], check=True, env=env,
+                           stdout=subprocess.DEVNULL)
+            tk = open(out2).read().split()
+            nv2, nc2 = int(tk[0]), int(tk[1])
+            c2 = np.array(tk[2 + 9 * nv2:], dtype=np.float64).reshape(nc2, 2)
+            ms2 = c2[:, 1] * 1e3
+            ours_same = lat[:nc2][solved[:nc2]]
+            line["reference_build_local_calls"] = {
+                "kind": "reference", "cores": 1, "calls": int(nc2), "p50_ms": float(np.percentile(ms2[2:], 50)),
+                "p99_ms": float(np.percentile(ms2[2:], 99)),
+                "ours_p50_ms_same_calls": float(np.percentile(ours_same, 50)) if ours_same.size else None,
+                "sample": f"the {nc2} local rotAvg(10) calls before the first loop closure; the reference's rotAvg + ral sources "
+                          "(oracle/_ref, -O2, dense stand-ins for SPQR / UMFPACK, eager stand-in for Eigen)",
+                "parity": "tests/test_rotavg.py::test_oracle_stream_vs_reference_build and test_stream_matches_oracle hold both "
+                          "sides to the same rotations"}
+    except Exception as e:                                   # noqa: BLE001
+        line["reference_build_local_calls"] = {"error": repr(e)[:200]}
     if args.cpu_frames > 0:
         k = 0
         sub = []
