@@ -112,6 +112,7 @@ struct ira_context {
   bool persistent = true;    // one cooperative kernel per linear solve
   bool pairing = false;      // 2x2 block-Jacobi active in the multi-kernel path
   int pcg_blocks_per_sm = 0;
+  int res_blocks_per_sm = 0;
   // matrix-in-shared-memory PCG (ira_pcg2.cuh): cached entry columns per slice, entries per block, usable flag
   std::vector<int> h_slice_width;
   int pcg2_wcap = 0, pcg2_entries = 0;
@@ -261,7 +262,13 @@ ira_status run_residual(ira_context* h, const double4* Qsrc, int store_theta) {
   if (h->m == 0) return IRA_OK;
   ProfScope ps(h, KC_RESIDUAL);
   const int ntiles = (int)(h->m_pad / kResTile);
-  const int grid = std::min(ntiles, h->sms * 8);
+  // persistent CTAs: exactly as many as are resident at once (a larger grid runs its tail as a second, half-empty wave)
+  if (h->res_blocks_per_sm == 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_residual, kResTile, 0) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 4; }
+    h->res_blocks_per_sm = nb;
+  }
+  const int grid = std::min(ntiles, h->sms * h->res_blocks_per_sm);
   k_residual<<<grid, kResTile, 0, h->stream>>>(h->I.as<int2>(), h->QQ.as<double>(), h->m_pad,
                                                h->weights.as<double>(), Qsrc, h->wres.as<double4>(),
                                                h->m, ntiles, store_theta);
