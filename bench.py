@@ -557,11 +557,14 @@ def run_ours(args):
             with open(tp) as fh:
                 traffic = json.load(fh)
         spmv_phase_us = ph.get("spmv_us_per_phase")
+        kname = {1: "k_pcg_persistent (vectors in HBM)", 2: "k_pcg_persistent_reg (state in registers)",
+                 3: "k_pcg_persistent_reg_mw", 4: "k_pcg_smem (state in registers, matrix in shared memory)",
+                 5: "k_pcg_peer*"}.get(pinfo.pcg_kernel, f"driver {pinfo.pcg_kernel}")
         roof = {
-            "kernel": "k_pcg_smem (persistent PCG solve: SELL SpMV with the matrix in shared memory + Chronopoulos-Gear PCG, "
-                      "3 RHS; one launch per IRLS iteration)",
+            "kernel": kname + ": persistent PCG solve (SELL SpMV + Chronopoulos-Gear PCG, 3 RHS); one launch per IRLS iteration",
+            "pcg_kernel_id": pinfo.pcg_kernel,
             "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "peak_source": peak_src, "traffic": (traffic or {}).get("k_pcg_smem"),
+            "peak_source": peak_src, "traffic": (traffic or {}).get("k_pcg_smem" if pinfo.pcg_kernel == 4 else "k_pcg_persistent_reg"),
             "algorithmic_bytes_per_launch": K * per_iter_bytes, "algorithmic_bytes_per_pcg_iteration": per_iter_bytes,
             "pcg_iterations_per_launch": K, "launch_us": launch_us, "launches_timed": pcg["launches"],
             "share_of_step": prof_share.get("pcg"),

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define IRA_ABI_VERSION 1
+#define IRA_ABI_VERSION 2
 
 typedef struct ira_context* ira_handle;
 
@@ -73,7 +73,8 @@ typedef struct ira_options {
                               lane would let them live in registers (A/B measurement);
                               +8 = one GPU only: the barrier-free kernel of the multi-GPU path
                               (self-validating data instead of grid barriers; measured slower, kept for A/B);
-                              +16 = do not use the matrix-in-shared-memory kernel (ira_pcg2.cuh; A/B)          */
+                              +32 = the matrix-in-shared-memory kernel (ira_pcg2.cuh; measured SLOWER: it leaves the SM
+                              28 KB of L1 and the gathers lose their memory-level parallelism; kept for A/B)   */
   int32_t spmv_variant;    /* experiment knob: gather flavour / unroll of the SELL SpMV (0 = default)  */
   int32_t small_path;      /* window-sized problems (n_total <= 64, 1 <= n_free <= 32, m <= 256) in
                               ira_l1ra_irls run as ONE single-block kernel with dense Cholesky solves
@@ -114,6 +115,11 @@ typedef struct ira_stats {
    * the vector-update phases, whole-kernel time, number of SpMV phases executed                   */
   int32_t n_pcg, pcg_spmv_phases;
   double  t_pcg_ms, pcg_spmv_ms, pcg_update_ms, pcg_kernel_ms;
+  /* which linear-solve driver ran (ABI 2): 0 one kernel per CG step, 1 k_pcg_persistent (vectors in HBM),
+   * 2 k_pcg_persistent_reg, 3 k_pcg_persistent_reg_mw, 4 k_pcg_smem (matrix in shared memory), 5 peer-memory kernels,
+   * 6 single-block window solver */
+  int32_t pcg_kernel;
+  int32_t reserved_stats;
 } ira_stats;
 
 ira_status  ira_options_default(ira_options* opt);
@@ -180,7 +186,8 @@ ira_status ira_resident_start(ira_handle h, int32_t mode);
  * (ral/test.cpp:288-300) do back to back.  Same arguments as the two calls; the rotations stay on the
  * device between the stages.  *runtime_s_out is the wall time of the whole call.  Window-sized problems
  * (see ira_options.small_path) take a single launch with exact dense solves; irls_stats then carries
- * irls_iters, the first 8 scores and kernel_launches = 1. */
+ * irls_iters, the first 8 scores and kernel_launches = 1.  irls_stats->cg_hit_max counts the linear solves of BOTH
+ * stages that stopped at cg_max_iters without reaching cg_rtol. */
 ira_status ira_l1ra_irls(ira_handle h, int64_t m, int64_t n_total, int32_t f,
                          const int32_t* I_pairs, const double* QQ, int64_t ld_qq,
                          double* Q, int64_t ld_q,

@@ -66,6 +66,7 @@ class Stats(C.Structure):
         ("n_pcg", C.c_int32), ("pcg_spmv_phases", C.c_int32),
         ("t_pcg_ms", C.c_double), ("pcg_spmv_ms", C.c_double), ("pcg_update_ms", C.c_double),
         ("pcg_kernel_ms", C.c_double),
+        ("pcg_kernel", C.c_int32), ("reserved_stats", C.c_int32),
     ]
 
 

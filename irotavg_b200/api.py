@@ -55,6 +55,7 @@ class IrlsInfo:
     upload_ms: float = 0.0
     download_ms: float = 0.0
     profile: dict = field(default_factory=dict)
+    pcg_kernel: int = 0
 
 
 def _info(st: Stats, iters: int, runtime: float) -> IrlsInfo:
@@ -72,7 +73,7 @@ def _info(st: Stats, iters: int, runtime: float) -> IrlsInfo:
                     cg_iters=list(st.cg_iters[:k]), cg_relres=list(st.cg_relres[:k]),
                     cg_hit_max=st.cg_hit_max, kernel_launches=st.kernel_launches,
                     device_ms=st.t_total_ms, upload_ms=st.t_upload_ms, download_ms=st.t_download_ms,
-                    profile=prof)
+                    profile=prof, pcg_kernel=st.pcg_kernel)
 
 
 class Solver:

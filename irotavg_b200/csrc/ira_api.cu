@@ -9,6 +9,7 @@
 #include <math.h>
 #include <nccl.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -141,6 +142,7 @@ struct ira_context {
   int prof_c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int launches = 0;
   int prev_cg = 0;
+  int pcg_kernel = 0;        // which linear-solve driver the last solve used (ira_stats.pcg_kernel)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -504,9 +506,10 @@ ira_status solve_pcg_persistent(ira_context* h) {
     const int g2 = std::max(1, cdiv(h->nslices, kMwGroups));
     IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_pcg_persistent_reg_mw, dim3(g2), dim3(kPcgThreads), rargs, 0, h->stream));
     h->launches++;
+    h->pcg_kernel = 3;
     return IRA_OK;
   }
-  if (h->pcg2_ok && !(h->opt.solver & (4 | 16)) && h->opt.spmv_variant == 0) {
+  if (h->pcg2_ok && (h->opt.solver & 32) && !(h->opt.solver & 4) && h->opt.spmv_variant == 0) {   // opt-in: measured slower
     // one row per lane, state in registers, the matrix in shared memory (ira_pcg2.cuh)
     Pcg2Params p2;
     p2.reg.base = pp;
@@ -514,8 +517,9 @@ ira_status solve_pcg_persistent(ira_context* h) {
     p2.wcap = h->pcg2_wcap; p2.smem_entries = h->pcg2_entries;
     void* rargs[] = {(void*)&p2};
     IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_pcg_smem, dim3(std::min(h->nslices, h->sms)), dim3(kPcg2Threads), rargs,
-                                            (size_t)h->pcg2_entries * 12 + 24 * kPcg2Threads, h->stream));
+                                            (size_t)h->pcg2_entries * 12 + 8 * kPcg2StateDoubles * kPcg2Threads, h->stream));
     h->launches++;
+    h->pcg_kernel = 4;
     return IRA_OK;
   }
   if (h->nslices <= grid * (kPcgThreads / 32) && !(h->opt.solver & 4)) {   // one row per lane: state in registers
@@ -531,6 +535,7 @@ ira_status solve_pcg_persistent(ira_context* h) {
     }
     IRA_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPcgThreads), rargs, 0, h->stream));
     h->launches++;
+    h->pcg_kernel = 2;
     return IRA_OK;
   }
   void* args[] = {(void*)&pp};
@@ -542,6 +547,7 @@ ira_status solve_pcg_persistent(ira_context* h) {
   }
   IRA_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPcgThreads), args, 0, h->stream));
   h->launches++;
+  h->pcg_kernel = 1;
   return IRA_OK;
 }
 
@@ -662,6 +668,7 @@ ira_status solve_pcg_peer(ira_context* h) {
   }
   IRA_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, 0, h->stream));
   h->launches++;
+  h->pcg_kernel = 5;
   const double4* xsrc = ll ? peer_window_ll_at((unsigned char*)h->peer_win.p, h->npos).X
                            : peer_window_at((unsigned char*)h->peer_win.p, h->peer_n).X;
   IRA_CUDA(h, cudaMemcpyAsync(h->X.p, xsrc, sizeof(double4) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
@@ -829,7 +836,13 @@ ira_status plan_pcg2(ira_context* h) {
   IRA_CUDA(h, cudaStreamSynchronize(h->stream));
   int wmax = 0;
   for (int w : h->h_slice_width) wmax = std::max(wmax, w);
-  const int cap = (kPcg2SmemBudget - 24 * kPcg2Threads) / 12;          // entries of (int col, double w2) beside x
+  int optin = 0;
+  cudaFuncAttributes fa;
+  if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device) != cudaSuccess ||
+      cudaFuncGetAttributes(&fa, k_pcg_smem) != cudaSuccess) { cudaGetLastError(); return IRA_OK; }
+  const int state_bytes = 8 * kPcg2StateDoubles * kPcg2Threads;
+  const int cap = (optin - (int)fa.sharedSizeBytes - state_bytes - 256) / 12;   // entries of (int col, double w2) beside x, p
+  if (cap < 4 * kSellC) return IRA_OK;
   int wcap = wmax, need = 0;
   for (;; wcap -= 4) {
     need = 0;
@@ -843,16 +856,22 @@ ira_status plan_pcg2(ira_context* h) {
   if (wcap < 4 && wmax >= 4) return IRA_OK;                            // nothing fits: not worth it
   h->pcg2_wcap = std::max(wcap, 0);
   h->pcg2_entries = std::max(need, kSellC);
-  const int bytes = h->pcg2_entries * 12 + 24 * kPcg2Threads;
-  if (cudaFuncSetAttribute(k_pcg_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
+  const int bytes = h->pcg2_entries * 12 + state_bytes;
+  const bool dbg = getenv("IRA_DEBUG") != nullptr;
+  cudaError_t ce = cudaFuncSetAttribute(k_pcg_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (ce != cudaSuccess) {
+    if (dbg) fprintf(stderr, "[ira] k_pcg_smem: %d B of dynamic shared memory refused: %s\n", bytes, cudaGetErrorString(ce));
     cudaGetLastError();
     return IRA_OK;
   }
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_smem, kPcg2Threads, (size_t)bytes) != cudaSuccess || nb < 1) {
+  ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_smem, kPcg2Threads, (size_t)bytes);
+  if (ce != cudaSuccess || nb < 1) {
+    if (dbg) fprintf(stderr, "[ira] k_pcg_smem: occupancy %d with %d B (%s)\n", nb, bytes, cudaGetErrorString(ce));
     cudaGetLastError();
     return IRA_OK;
   }
+  if (dbg) fprintf(stderr, "[ira] k_pcg_smem planned: wcap %d, %d entries, %d B per block\n", h->pcg2_wcap, h->pcg2_entries, bytes);
   h->pcg2_ok = true;
   return IRA_OK;
 }
@@ -1026,7 +1045,7 @@ ira_status ira_problem_upload(ira_handle h, int64_t m, int64_t n_total, int32_t 
                   n_total < (int64_t)h->opt.peer_min_rows && !h->fmt_csr && h->pcg_blocks_per_sm > 0;
   const bool one_gpu = h->opt.world_size <= 1 || h->replicated;
   h->pcg2_ok = false;
-  if (!h->fmt_csr && one_gpu) IRA_TRY(plan_pcg2(h));
+  if (!h->fmt_csr && one_gpu && (h->opt.solver & 32)) IRA_TRY(plan_pcg2(h));
   h->persistent = !h->fmt_csr && one_gpu && ((h->opt.solver & 3) != 1 || h->replicated) && h->pcg_blocks_per_sm > 0;
   h->peer = false;
   if ((h->opt.world_size > 1 && !h->replicated && (h->opt.shard_mode == 1 || h->opt.shard_mode == 2)) ||
@@ -1131,6 +1150,7 @@ ira_status ira_irls_resident(ira_handle h, int32_t cost, double sigma, int32_t m
   if (runtime_s_out) *runtime_s_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (stats) {
     stats->irls_iters = iters;
+    stats->pcg_kernel = (h->persistent || h->peer) ? h->pcg_kernel : 0;
     stats->t_total_ms = ms;
     stats->kernel_launches = h->launches - launches0;
     const Ctl& c = *h->h_ctl;
@@ -1698,6 +1718,7 @@ ira_status small_l1ra_irls(ira_context* h, int m, int n, int f, const int32_t* I
     memset(st, 0, sizeof *st);
     st->irls_iters = oh->irls_iters;
     st->kernel_launches = 1;
+    st->pcg_kernel = 6;
     for (int k = 0; k < std::min(oh->irls_iters, kSmScores); ++k) st->score[k] = oh->irls_score[k];
   }
   if (oh->nonfinite) { h->err = "score became non-finite"; return IRA_ERR_NONFINITE; }
@@ -1723,11 +1744,13 @@ extern "C" ira_status ira_l1ra_irls(ira_handle h, int64_t m, int64_t n_total, in
     return rs;
   }
   IRA_TRY(ira_problem_upload(h, m, n_total, f, I_pairs, QQ, ld_qq, Q, ld_q));
-  ira_status rc = ira_l1ra_resident(h, l1_max_iters, l1_change_th, l1_iters_out, nullptr, nullptr);
+  static thread_local ira_stats l1_stats;                  // only its non-convergence count is passed on
+  ira_status rc = ira_l1ra_resident(h, l1_max_iters, l1_change_th, l1_iters_out, nullptr, &l1_stats);
   if (rc != IRA_OK && rc != IRA_ERR_NONFINITE) return rc;
   h->start_mode = 1;                                       // irls continues from l1ra's rotations
   rc = ira_irls_resident(h, cost, sigma, irls_max_iters, irls_change_th, irls_iters_out, nullptr, irls_stats);
   h->start_mode = 0;
+  if (irls_stats) irls_stats->cg_hit_max += l1_stats.cg_hit_max;   // unconverged Newton solves of the l1ra stage count too
   if (rc != IRA_OK && rc != IRA_ERR_NONFINITE) return rc;
   IRA_TRY(ira_problem_download(h, Q, ld_q, weights));
   if (runtime_s_out) *runtime_s_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

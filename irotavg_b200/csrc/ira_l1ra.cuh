@@ -523,28 +523,7 @@ k_pcg_persistent_w3(const PcgW3Params p) {
       }
     }
     pcg_grid_reduce(v, p.partials, grid, red, tot);
-    if (threadIdx.x == 0) {
-      bool conv = true;
-      for (int c = 0; c < 3; ++c) {
-        sc_rr[c] = v[6 + c];
-        if (!(v[6 + c] <= p.rtol2 * sc_bb[c])) conv = false;
-      }
-      if (conv || it >= p.max_iters) {
-        sc_stop = 1;
-      } else {
-        for (int c = 0; c < 3; ++c) {
-          const double gam = v[c], del = v[3 + c];
-          double beta = 0.0, den = del;
-          if (it > 0) {
-            beta = sc_go[c] > 0.0 ? gam / sc_go[c] : 0.0;
-            if (sc_ao[c] != 0.0) den = del - beta * gam / sc_ao[c];
-          }
-          const double alpha = den > 0.0 ? gam / den : 0.0;
-          sc_go[c] = gam; sc_ao[c] = alpha; sc_a[c] = alpha; sc_b[c] = beta;
-        }
-      }
-    }
-    __syncthreads();
+    pcg_coefficients(tot, it, p.max_iters, p.rtol2, sc_bb, sc_go, sc_ao, sc_a, sc_b, sc_rr, &sc_stop);
     if (sc_stop) break;
     const double a0 = sc_a[0], a1 = sc_a[1], a2 = sc_a[2], b0 = sc_b[0], b1 = sc_b[1], b2 = sc_b[2];
     for (int s = gwarp; s < p.nslices; s += nwarps) {

@@ -92,16 +92,38 @@ k_mst_labels(const int2* __restrict__ I, int64_t m, unsigned long long* label, M
     bool moved = false;
     for (int64_t sg = gwarp; sg < nseg; sg += nwarps) {
       const int64_t s0 = sg * kMstSeg, s1 = min(m, s0 + (int64_t)kMstSeg);
+      int2 e_next = make_int2(0, 0);                           // edge endpoints are prefetched one group ahead
+      if (s0 + lane < s1) e_next = __ldg(I + s0 + lane);
       for (int64_t k0 = s0; k0 < s1; k0 += 32) {
         const int64_t k = k0 + lane;
-        int2 e = make_int2(0, 0);
+        const int2 e = k < s1 ? e_next : make_int2(0, 0);       // lanes past the segment end hold no edge
+        if (k + 32 < s1) e_next = __ldg(I + k + 32);
         unsigned long long tu = kMstInf, tv = kMstInf;
-        if (k < s1) {
-          e = __ldg(I + k);
-          if (e.x != e.y) { tu = __ldcg(label + e.x); tv = __ldcg(label + e.y); }
-        }
+        if (k < s1 && e.x != e.y) { tu = __ldcg(label + e.x); tv = __ldcg(label + e.y); }
         const unsigned long long k1 = (unsigned long long)k + 1ull;
-        // relax the group to its local fixed point: the lowest lane that can improve a label goes first
+        // Fast path for chains laid out in edge order (edge j starts where edge j-1 ended, indices increasing): the
+        // time stamps of a whole run follow from its head in log2(32) steps.  next(next(t, k), k') = (sweep of
+        // next(t, k), k') for k' > k, so only the SWEEP travels down the run: a segmented min-scan.
+        {
+          const int ey_left = __shfl_up_sync(0xffffffffu, e.y, 1);
+          const bool valid = k < s1 && e.x != e.y;
+          bool head = !(lane > 0 && valid && e.x == ey_left);
+          unsigned int sw = (valid && tu != kMstInf) ? (unsigned int)(mst_next(tu, k1) >> 32) : 0xffffffffu;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int swl = __shfl_up_sync(0xffffffffu, sw, d);
+            const bool hl = __shfl_up_sync(0xffffffffu, (int)head, d) != 0;
+            if (lane >= d && !head) { sw = min(sw, swl); head = hl; }
+          }
+          if (valid && sw != 0xffffffffu) {
+            const unsigned long long cand = ((unsigned long long)sw << 32) | k1;
+            if (cand < tv) { atomicMin(label + e.y, cand); tv = cand; moved = true; }
+          }
+          const unsigned long long tvl = __shfl_up_sync(0xffffffffu, tv, 1);     // the left neighbour's end = my start
+          if (lane > 0 && valid && e.x == ey_left && tvl < tu) tu = tvl;
+        }
+        // whatever is left (backward edges, nodes shared otherwise): relax the group to its local fixed point, the
+        // lowest lane that can improve a label goes first
         unsigned int can = __ballot_sync(0xffffffffu, mst_can(tu, tv, k1));
         while (can) {
           const int j = __ffs(can) - 1;
@@ -130,7 +152,7 @@ k_mst_labels(const int2* __restrict__ I, int64_t m, unsigned long long* label, M
         }
       }
     }
-    if (moved && lane == 0) atomicOr(&ctl->changed[slot], 1);
+    if (__any_sync(0xffffffffu, moved) && lane == 0) atomicOr(&ctl->changed[slot], 1);
     grid.sync();
     if (!__ldcg(&ctl->changed[slot])) break;
   }

@@ -487,6 +487,42 @@ __device__ __forceinline__ void pcg_grid_reduce(double (&v)[kPcgNV], double* par
   for (int k = 0; k < kPcgNV; ++k) v[k] = tot[k];
 }
 
+// Chronopoulos-Gear coefficients of one iteration from the reduced totals (in shared memory, as pcg_grid_reduce
+// leaves them) v = {r.u (3), u.Au (3), |r|^2 (3)}: lanes
+// 0..2 of the block own one right-hand side each (three division chains side by side instead of nine in a row); every
+// block computes the same numbers from the same block-ordered totals.  A column that has converged
+// (|r_c| <= rtol |b_c|) is FROZEN: alpha_c = beta_c = 0 from then on, so its solution stays bit-fixed while the others
+// finish (round-off in gamma / delta of a converged column cannot perturb it any more).  Raises *sc_stop when all three
+// are frozen or the iteration cap is reached.  Ends with a block barrier.
+__device__ __forceinline__ void pcg_coefficients(const double* v /* shared: the 9 totals */, int it, int max_iters, double rtol2, double* sc_bb,
+                                                 double* sc_go, double* sc_ao, double* sc_a, double* sc_b, double* sc_rr,
+                                                 int* sc_stop) {
+  __shared__ int frozen[3];
+  if (threadIdx.x < 3) {
+    const int c = threadIdx.x;
+    if (it == 0) frozen[c] = !(sc_bb[c] > 0.0);                 // zero right-hand side: x_c = 0
+    if (!frozen[c]) {
+      sc_rr[c] = v[6 + c];
+      if (v[6 + c] <= rtol2 * sc_bb[c]) frozen[c] = 1;
+    }
+    double alpha = 0.0, beta = 0.0;
+    if (!frozen[c]) {
+      const double gam = v[c], del = v[3 + c];
+      double den = del;
+      if (it > 0) {
+        beta = sc_go[c] > 0.0 ? gam / sc_go[c] : 0.0;
+        if (sc_ao[c] != 0.0) den = del - beta * gam / sc_ao[c];
+      }
+      alpha = den > 0.0 ? gam / den : 0.0;
+      sc_go[c] = gam; sc_ao[c] = alpha;
+    }
+    sc_a[c] = alpha; sc_b[c] = beta;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && ((frozen[0] && frozen[1] && frozen[2]) || it >= max_iters)) *sc_stop = 1;
+  __syncthreads();
+}
+
 template <int V, int UNR>
 __global__ void __launch_bounds__(kPcgThreads, 1)
 k_pcg_persistent(const PcgParams p) {
@@ -570,28 +606,7 @@ k_pcg_persistent(const PcgParams p) {
     pcg_grid_reduce(v, p.partials, grid, red, tot);
     if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; }
     // ---- Chronopoulos-Gear coefficients (thread 0; identical in every block) ---------------------
-    if (threadIdx.x == 0) {
-      bool conv = true;
-      for (int c = 0; c < 3; ++c) {
-        sc_rr[c] = v[6 + c];
-        if (!(v[6 + c] <= p.rtol2 * sc_bb[c])) conv = false;
-      }
-      if (conv || it >= p.max_iters) {
-        sc_stop = 1;
-      } else {
-        for (int c = 0; c < 3; ++c) {
-          const double gam = v[c], del = v[3 + c];
-          double beta = 0.0, den = del;
-          if (it > 0) {
-            beta = sc_go[c] > 0.0 ? gam / sc_go[c] : 0.0;
-            if (sc_ao[c] != 0.0) den = del - beta * gam / sc_ao[c];
-          }
-          const double alpha = den > 0.0 ? gam / den : 0.0;
-          sc_go[c] = gam; sc_ao[c] = alpha; sc_a[c] = alpha; sc_b[c] = beta;
-        }
-      }
-    }
-    __syncthreads();
+    pcg_coefficients(tot, it, p.max_iters, p.rtol2, sc_bb, sc_go, sc_ao, sc_a, sc_b, sc_rr, &sc_stop);
     if (sc_stop) break;
     const double a0 = sc_a[0], a1 = sc_a[1], a2 = sc_a[2], b0 = sc_b[0], b1 = sc_b[1], b2 = sc_b[2];
     // ---- p = u + beta p; s = w + beta s; x += alpha p; r -= alpha s; u = M^-1 r ----------------------
@@ -744,28 +759,7 @@ k_pcg_persistent_reg(const PcgRegParams q) {
     }
     pcg_grid_reduce(v, p.partials, grid, red, tot);
     if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; }
-    if (threadIdx.x == 0) {
-      bool conv = true;
-      for (int c = 0; c < 3; ++c) {
-        sc_rr[c] = v[6 + c];
-        if (!(v[6 + c] <= p.rtol2 * sc_bb[c])) conv = false;
-      }
-      if (conv || it >= p.max_iters) {
-        sc_stop = 1;
-      } else {
-        for (int c = 0; c < 3; ++c) {
-          const double gam = v[c], del = v[3 + c];
-          double beta = 0.0, den = del;
-          if (it > 0) {
-            beta = sc_go[c] > 0.0 ? gam / sc_go[c] : 0.0;
-            if (sc_ao[c] != 0.0) den = del - beta * gam / sc_ao[c];
-          }
-          const double alpha = den > 0.0 ? gam / den : 0.0;
-          sc_go[c] = gam; sc_ao[c] = alpha; sc_a[c] = alpha; sc_b[c] = beta;
-        }
-      }
-    }
-    __syncthreads();
+    pcg_coefficients(tot, it, p.max_iters, p.rtol2, sc_bb, sc_go, sc_ao, sc_a, sc_b, sc_rr, &sc_stop);
     if (sc_stop) break;
     const double a0 = sc_a[0], a1 = sc_a[1], a2 = sc_a[2], b0 = sc_b[0], b1 = sc_b[1], b2 = sc_b[2];
     if (row >= 0) {
@@ -927,28 +921,7 @@ k_pcg_persistent_reg_mw(const PcgRegParams q) {
     }
     pcg_grid_reduce(v, p.partials, grid, red, tot);
     if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; dbg[1] += c - dm; dm = c; }
-    if (threadIdx.x == 0) {
-      bool conv = true;
-      for (int c = 0; c < 3; ++c) {
-        sc_rr[c] = v[6 + c];
-        if (!(v[6 + c] <= p.rtol2 * sc_bb[c])) conv = false;
-      }
-      if (conv || it >= p.max_iters) {
-        sc_stop = 1;
-      } else {
-        for (int c = 0; c < 3; ++c) {
-          const double gam = v[c], del = v[3 + c];
-          double beta = 0.0, den = del;
-          if (it > 0) {
-            beta = sc_go[c] > 0.0 ? gam / sc_go[c] : 0.0;
-            if (sc_ao[c] != 0.0) den = del - beta * gam / sc_ao[c];
-          }
-          const double alpha = den > 0.0 ? gam / den : 0.0;
-          sc_go[c] = gam; sc_ao[c] = alpha; sc_a[c] = alpha; sc_b[c] = beta;
-        }
-      }
-    }
-    __syncthreads();
+    pcg_coefficients(tot, it, p.max_iters, p.rtol2, sc_bb, sc_go, sc_ao, sc_a, sc_b, sc_rr, &sc_stop);
     if (timer) { const long long c = clock64(); dbg[2] += c - dm; dm = c; }
     if (sc_stop) break;
     const double a0 = sc_a[0], a1 = sc_a[1], a2 = sc_a[2], b0 = sc_b[0], b1 = sc_b[1], b2 = sc_b[2];

@@ -9,7 +9,16 @@
 // own.  So each block copies its slices' (col, w2) once per solve (26 MB read from L2/HBM once, coalesced) and
 // every iteration's SpMV reads them from shared memory: only the random gathers of u and the 32 B/row store of
 // the new u still touch L2.  Without the software pipeline of the global streams the kernel also needs ~20 fewer
-// registers: no spills at 88 registers x 704 threads (build.log), where k_pcg_persistent_reg spilled 360 B.
+// registers (and x, p move to shared memory too): no spills at the 80 registers 22 warps per SM leave (build.log),
+// where k_pcg_persistent_reg spilled 360 B.
+//
+// MEASURED RESULT (B200, config 3, L1, 30 IRLS iterations, profiles/r02_ab_pcg2_smem.json): 78 ms per step against
+// 52 ms for k_pcg_persistent_reg - SLOWER, so this kernel is opt-in (ira_options.solver & 32) and documents the
+// experiment.  Why: a block that owns 227 KB of shared memory leaves the SM ~28 KB of L1, and on sm_100 every
+// outstanding global load holds an L1 line: the ~2 800 gathers a block wants in flight no longer fit, and the SpMV
+// phase turns latency bound.  The 26 MB of streams it saves were worth at most ~1.5 us of the 15 us phase.
+// (Also measured on the way: 22 warps per SM leave 80 registers per thread, not 88 - 6 warps per SM sub-partition
+// share its 16 384 registers - so 704 threads buy nothing over 768.)
 //
 // Everything else is the single-reduction (Chronopoulos-Gear) PCG of ira_pcg.cuh with the exact 2x2 / 3x3 block
 // preconditioner, one row per lane, x r p s in registers.  Differences:
@@ -17,8 +26,10 @@
 //     dependent FP64 divisions, ~1.1 us per iteration);
 //   * a column that has converged (|r_c| <= rtol |b_c|) is FROZEN: alpha_c = beta_c = 0 from then on, so its
 //     solution stays bit-fixed while the other columns finish (round-off in gamma/delta of a converged column
-//     can no longer perturb it);
-//   * padding slots (w2 = 0) do not issue their gather.
+//     can no longer perturb it).
+// (Padding slots, col = row and w2 = 0, still issue their gather: predicating it put every gather behind a divergent
+// branch whose other side rewrites the destination registers - the warp then waits for each load in turn; measured
+// 37 us per PCG iteration instead of 22.)
 // If a block's slices do not fit, every slice keeps its first `wcap` entry columns in shared memory and reads
 // the rest from global memory (graphs up to ~113 664 rows per GPU; larger ones use k_pcg_persistent).
 #pragma once
@@ -26,9 +37,9 @@
 
 namespace ira {
 
-constexpr int kPcg2Threads = 704;                 // 22 warps: 148 x 22 = 3 256 slices >= 3 125 (config 3), <= 93 registers
+constexpr int kPcg2Threads = 704;                 // 22 warps: 148 x 22 = 3 256 slices >= 3 136 (config 3)
 constexpr int kPcg2Warps = kPcg2Threads / 32;
-constexpr int kPcg2SmemBudget = 226 * 1024;       // dynamic shared memory for the cached matrix (227 KB max per block)
+constexpr int kPcg2StateDoubles = 6;              // x and p of every thread live in shared memory
 
 struct Pcg2Params {
   PcgRegParams reg;
@@ -36,7 +47,7 @@ struct Pcg2Params {
   int smem_entries;    // capacity check (entries of 12 B)
 };
 
-__global__ void __maxnreg__(88)
+__global__ void __launch_bounds__(kPcg2Threads, 1)
 k_pcg_smem(const Pcg2Params q2) {
   const PcgRegParams& q = q2.reg;
   const PcgParams& p = q.base;
@@ -45,7 +56,6 @@ k_pcg_smem(const Pcg2Params q2) {
   __shared__ double red[kPcgNV * 32];
   __shared__ double tot[kPcgNV];
   __shared__ double sc_bb[3], sc_go[3], sc_ao[3], sc_a[3], sc_b[3], sc_rr[3];
-  __shared__ int sc_frozen[3];
   __shared__ int sc_stop;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slice = blockIdx.x + gridDim.x * warp;                   // <= 1 slice per warp
@@ -64,9 +74,11 @@ k_pcg_smem(const Pcg2Params q2) {
     const int s = blockIdx.x + gridDim.x * w;
     if (s < p.nslices) off += min(p.slice_width[s], q2.wcap) * kSellC;
   }
-  // dynamic shared memory: x (3 x blockDim doubles: the solution only accumulates, nobody else reads it) | w2 | col
+  // dynamic shared memory: x and p (6 x blockDim doubles: private to their thread, kept out of the 80-register budget
+  // that 22 warps per SM leave - 6 warps per SM sub-partition x 32 lanes x 80 registers of its 16 384) | w2 | col
   double* const xs = reinterpret_cast<double*>(dyn_smem) + threadIdx.x;
-  double* const w2s = reinterpret_cast<double*>(dyn_smem) + 3 * kPcg2Threads;   // [smem_entries]
+  double* const ps = xs + 3 * kPcg2Threads;
+  double* const w2s = reinterpret_cast<double*>(dyn_smem) + kPcg2StateDoubles * kPcg2Threads;   // [smem_entries]
   int* const cols = reinterpret_cast<int*>(w2s + q2.smem_entries);
   for (int j = 0; j < cw; ++j) {                                      // coalesced 128 B / 256 B lines
     const int64_t o = base + (int64_t)j * kSellC;
@@ -80,9 +92,10 @@ k_pcg_smem(const Pcg2Params q2) {
   double v[kPcgNV];
 #pragma unroll
   for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
-  double r0 = 0, r1 = 0, r2 = 0, p0 = 0, p1 = 0, p2 = 0, s0 = 0, s1 = 0, s2 = 0;
+  double r0 = 0, r1 = 0, r2 = 0, s0 = 0, s1 = 0, s2 = 0;
   double u0 = 0, u1 = 0, u2 = 0, di = 0;
   xs[0] = 0.0; xs[kPcg2Threads] = 0.0; xs[2 * kPcg2Threads] = 0.0;
+  ps[0] = 0.0; ps[kPcg2Threads] = 0.0; ps[2 * kPcg2Threads] = 0.0;
   if (row >= 0) {
     const double4 b = ldg256(p.B + row);
     const double d = p.diag[row];
@@ -112,7 +125,6 @@ k_pcg_smem(const Pcg2Params q2) {
   if (threadIdx.x < 3) {
     const int c = threadIdx.x;
     sc_bb[c] = v[c]; sc_rr[c] = v[c]; sc_go[c] = 1.0; sc_ao[c] = 1.0; sc_a[c] = 0.0; sc_b[c] = 0.0;
-    sc_frozen[c] = !(v[c] > 0.0);                                    // zero right-hand side: x_c = 0
   }
   if (threadIdx.x == 0) sc_stop = !(v[0] > 0.0 || v[1] > 0.0 || v[2] > 0.0);
   __syncthreads();
@@ -132,7 +144,7 @@ k_pcg_smem(const Pcg2Params q2) {
 #pragma unroll
         for (int t = 0; t < 4; ++t) { c[t] = mycols[(j + t) * kSellC]; ww[t] = myw2[(j + t) * kSellC]; }
 #pragma unroll
-        for (int t = 0; t < 4; ++t) g[t] = ww[t] != 0.0 ? ld256(p.U + c[t]) : make_double4(u0, u1, u2, 0.0);
+        for (int t = 0; t < 4; ++t) g[t] = ld256(p.U + c[t]);
 #pragma unroll
         for (int t = 0; t < 4; ++t) { w0 += ww[t] * (u0 - g[t].x); w1 += ww[t] * (u1 - g[t].y); w2 += ww[t] * (u2 - g[t].z); }
       }
@@ -144,7 +156,7 @@ k_pcg_smem(const Pcg2Params q2) {
           c[t] = __ldg(p.sell_col + o); ww[t] = __ldg(p.sell_w2 + o);
         }
 #pragma unroll
-        for (int t = 0; t < 4; ++t) g[t] = ww[t] != 0.0 ? ld256(p.U + c[t]) : make_double4(u0, u1, u2, 0.0);
+        for (int t = 0; t < 4; ++t) g[t] = ld256(p.U + c[t]);
 #pragma unroll
         for (int t = 0; t < 4; ++t) { w0 += ww[t] * (u0 - g[t].x); w1 += ww[t] * (u1 - g[t].y); w2 += ww[t] * (u2 - g[t].z); }
       }
@@ -160,32 +172,12 @@ k_pcg_smem(const Pcg2Params q2) {
     }
     pcg_grid_reduce(v, p.partials, grid, red, tot);
     if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; }
-    // ---- Chronopoulos-Gear coefficients: lane c of warp 0 owns column c (identical in every block) ---------
-    if (threadIdx.x < 3) {
-      const int c = threadIdx.x;
-      const double rr = v[6 + c];
-      sc_rr[c] = sc_frozen[c] ? sc_rr[c] : rr;
-      if (!sc_frozen[c] && rr <= p.rtol2 * sc_bb[c]) sc_frozen[c] = 1;
-      double alpha = 0.0, beta = 0.0;
-      if (!sc_frozen[c]) {
-        const double gam = v[c], del = v[3 + c];
-        double den = del;
-        if (it > 0) {
-          beta = sc_go[c] > 0.0 ? gam / sc_go[c] : 0.0;
-          if (sc_ao[c] != 0.0) den = del - beta * gam / sc_ao[c];
-        }
-        alpha = den > 0.0 ? gam / den : 0.0;
-        sc_go[c] = gam; sc_ao[c] = alpha;
-      }
-      sc_a[c] = alpha; sc_b[c] = beta;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && ((sc_frozen[0] && sc_frozen[1] && sc_frozen[2]) || it >= p.max_iters)) sc_stop = 1;
-    __syncthreads();
+    pcg_coefficients(tot, it, p.max_iters, p.rtol2, sc_bb, sc_go, sc_ao, sc_a, sc_b, sc_rr, &sc_stop);
     if (sc_stop) break;
     const double a0 = sc_a[0], a1 = sc_a[1], a2 = sc_a[2], b0 = sc_b[0], b1 = sc_b[1], b2 = sc_b[2];
     if (row >= 0) {
-      p0 = u0 + b0 * p0; p1 = u1 + b1 * p1; p2 = u2 + b2 * p2;
+      const double p0 = u0 + b0 * ps[0], p1 = u1 + b1 * ps[kPcg2Threads], p2 = u2 + b2 * ps[2 * kPcg2Threads];
+      ps[0] = p0; ps[kPcg2Threads] = p1; ps[2 * kPcg2Threads] = p2;
       s0 = w0 + b0 * s0; s1 = w1 + b1 * s1; s2 = w2 + b2 * s2;
       xs[0] += a0 * p0; xs[kPcg2Threads] += a1 * p1; xs[2 * kPcg2Threads] += a2 * p2;
       r0 -= a0 * s0; r1 -= a1 * s1; r2 -= a2 * s2;

@@ -118,7 +118,7 @@ __device__ __forceinline__ void peer_barrier(const PcgPeerParams& q, cooperative
         else if (now - t0 > 20000000000ull) asm volatile("trap;");
       }
     }
-    __threadfence();     // acquire: drop stale L1 lines; the peers' data is already in this GPU's L2 (its home)
+    __threadfence_system();   // acquire at SYSTEM scope (the releasing stores came from other GPUs): also drops stale L1 lines
   }
   __syncthreads();
 }
@@ -246,28 +246,7 @@ k_pcg_peer(const PcgPeerParams q) {
 #pragma unroll
     for (int k = 0; k < kPcgNV; ++k) v[k] = tot[k];
     if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; }
-    if (threadIdx.x == 0) {
-      bool conv = true;
-      for (int c = 0; c < 3; ++c) {
-        sc_rr[c] = v[6 + c];
-        if (!(v[6 + c] <= p.rtol2 * sc_bb[c])) conv = false;
-      }
-      if (conv || it >= p.max_iters) {
-        sc_stop = 1;
-      } else {
-        for (int c = 0; c < 3; ++c) {
-          const double gam = v[c], del = v[3 + c];
-          double beta = 0.0, den = del;
-          if (it > 0) {
-            beta = sc_go[c] > 0.0 ? gam / sc_go[c] : 0.0;
-            if (sc_ao[c] != 0.0) den = del - beta * gam / sc_ao[c];
-          }
-          const double alpha = den > 0.0 ? gam / den : 0.0;
-          sc_go[c] = gam; sc_ao[c] = alpha; sc_a[c] = alpha; sc_b[c] = beta;
-        }
-      }
-    }
-    __syncthreads();
+    pcg_coefficients(tot, it, p.max_iters, p.rtol2, sc_bb, sc_go, sc_ao, sc_a, sc_b, sc_rr, &sc_stop);
     if (sc_stop) break;
     const double a0 = sc_a[0], a1 = sc_a[1], a2 = sc_a[2], b0 = sc_b[0], b1 = sc_b[1], b2 = sc_b[2];
     // ---- phase B: my rows of p, s, x, r, u; u goes to every rank, (r, s) of paired rows to the mate's owner ----
@@ -397,15 +376,21 @@ __device__ __forceinline__ double4 ld_tagged(const double4* ptr, int p) {
   }
   return v;
 }
+// A dot-product slot is {value, epoch}.  PTX does not promise that a 16-byte vector access is single-copy atomic
+// (it may be performed as two scalars), so the pair is published with release / acquire on the epoch word instead of
+// one v2 store: value first (relaxed), then the epoch with st.release.sys; the reader polls the epoch with
+// ld.acquire.sys and only then reads the value.  The slot is reused two iterations later, by which time every
+// reader has consumed it (a rank publishes iteration k + 2 only after it has everybody's sums of k + 1).
 __device__ __forceinline__ void st_dot16(double* slot, double v, unsigned long long epoch) {
-  asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" :: "l"(slot), "l"(__double_as_longlong(v)), "l"(epoch) : "memory");
+  asm volatile("st.relaxed.sys.global.b64 [%0], %1;" :: "l"(slot), "l"(__double_as_longlong(v)) : "memory");
+  asm volatile("st.release.sys.global.b64 [%0], %1;" :: "l"(slot + 1), "l"(epoch) : "memory");
 }
 __device__ __forceinline__ double ld_dot16(const double* slot, unsigned long long epoch) {
   long long v; unsigned long long e;
   unsigned long long t0 = 0;
   unsigned int spins = 0;
   for (;;) {
-    asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(v), "=l"(e) : "l"(slot) : "memory");
+    asm volatile("ld.acquire.sys.global.b64 %0, [%1];" : "=l"(e) : "l"(slot + 1) : "memory");
     if (e == epoch) break;
     if ((++spins & 0xfffu) == 0u) {
       unsigned long long now;
@@ -414,6 +399,7 @@ __device__ __forceinline__ double ld_dot16(const double* slot, unsigned long lon
       else if (now - t0 > 20000000000ull) asm volatile("trap;");
     }
   }
+  asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
   return __longlong_as_double(v);
 }
 
@@ -622,28 +608,7 @@ k_pcg_peer_ll(const PcgPeerParams q) {
 #pragma unroll
     for (int k = 0; k < kPcgNV; ++k) v[k] = tot[k];
     if (timer) { const long long c = clock64(); c_spmv += c - c_mark; c_mark = c; d_dot += c - d_t; }
-    if (threadIdx.x == 0) {
-      bool conv = true;
-      for (int c = 0; c < 3; ++c) {
-        sc_rr[c] = v[6 + c];
-        if (!(v[6 + c] <= p.rtol2 * sc_bb[c])) conv = false;
-      }
-      if (conv || it >= p.max_iters) {
-        sc_stop = 1;
-      } else {
-        for (int c = 0; c < 3; ++c) {
-          const double gam = v[c], del = v[3 + c];
-          double beta = 0.0, den = del;
-          if (it > 0) {
-            beta = sc_go[c] > 0.0 ? gam / sc_go[c] : 0.0;
-            if (sc_ao[c] != 0.0) den = del - beta * gam / sc_ao[c];
-          }
-          const double alpha = den > 0.0 ? gam / den : 0.0;
-          sc_go[c] = gam; sc_ao[c] = alpha; sc_a[c] = alpha; sc_b[c] = beta;
-        }
-      }
-    }
-    __syncthreads();
+    pcg_coefficients(tot, it, p.max_iters, p.rtol2, sc_bb, sc_go, sc_ao, sc_a, sc_b, sc_rr, &sc_stop);
     if (sc_stop) break;
     const double a0 = sc_a[0], a1 = sc_a[1], a2 = sc_a[2], b0 = sc_b[0], b1 = sc_b[1], b2 = sc_b[2];
     // ---- phase B: my rows of p, s, x, r, u; the new u (parity of the NEXT iteration) goes to every rank ----
@@ -900,28 +865,7 @@ k_pcg_peer_ll_reg(const PcgPeerParams q) {
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kPcgNV; ++k) v[k] = totx[k];
-    if (threadIdx.x == 0) {
-      bool conv = true;
-      for (int c = 0; c < 3; ++c) {
-        sc_rr[c] = v[6 + c];
-        if (!(v[6 + c] <= p.rtol2 * sc_bb[c])) conv = false;
-      }
-      if (conv || it >= p.max_iters) {
-        sc_stop = 1;
-      } else {
-        for (int c = 0; c < 3; ++c) {
-          const double gam = v[c], del = v[3 + c];
-          double beta = 0.0, den = del;
-          if (it > 0) {
-            beta = sc_go[c] > 0.0 ? gam / sc_go[c] : 0.0;
-            if (sc_ao[c] != 0.0) den = del - beta * gam / sc_ao[c];
-          }
-          const double alpha = den > 0.0 ? gam / den : 0.0;
-          sc_go[c] = gam; sc_ao[c] = alpha; sc_a[c] = alpha; sc_b[c] = beta;
-        }
-      }
-    }
-    __syncthreads();
+    pcg_coefficients(totx, it, p.max_iters, p.rtol2, sc_bb, sc_go, sc_ao, sc_a, sc_b, sc_rr, &sc_stop);
     if (sc_stop) break;
     const double a0 = sc_a[0], a1 = sc_a[1], a2 = sc_a[2], b0 = sc_b[0], b1 = sc_b[1], b2 = sc_b[2];
     // ---- phase B (registers) ----

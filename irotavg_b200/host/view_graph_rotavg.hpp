@@ -183,13 +183,17 @@ inline RotAvgReport rot_avg(std::vector<ViewT*>& views, const std::vector<bool>&
 
   if (!h) h = detail_rotavg::handle();
   int32_t l1_out = 0, irls_out = 0;
+  static ira_stats st;                                     // the reference's solves are exact: an unconverged one is reported
   ira_status s = ira_l1ra_irls(h, m, nv, f, I.data(), QQ.data(), m, Q.data(), nv, prm.l1_iters, prm.change_th,
                                prm.cost, prm.sigma, prm.irls_iters, prm.change_th, weights.data(), &l1_out,
-                               &irls_out, &rep.seconds, nullptr);
+                               &irls_out, &rep.seconds, &st);
   if (s != IRA_OK && s != IRA_ERR_NONFINITE) {
     std::cerr << "rotAvg failed: " << ira_status_string(s) << ": " << ira_last_error(h) << std::endl;
     std::exit(-1);
   }
+  if (st.cg_hit_max > 0)
+    std::cerr << "irotavg-b200 WARNING: rotAvg: " << st.cg_hit_max << " linear solve(s) stopped at the PCG iteration cap "
+              << "without reaching cg_rtol; the step is inexact where the reference's is exact." << std::endl;
   rep.l1_iters = l1_out;
   rep.irls_iters = irls_out;
   rep.solved = true;

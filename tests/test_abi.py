@@ -48,7 +48,7 @@ def test_struct_layout_matches_ctypes(tmp_path, built_lib):
 
 def test_header_is_plain_c(tmp_path):
     prog = tmp_path / "c.c"
-    prog.write_text('#include "ira.h"\nint main(void){ira_options o; (void)o; return IRA_ABI_VERSION - 1;}\n')
+    prog.write_text('#include "ira.h"\nint main(void){ira_options o; (void)o; return IRA_ABI_VERSION - 2;}\n')
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c",
                     str(prog), "-o", str(tmp_path / "c.o")], check=True)
 
@@ -56,7 +56,7 @@ def test_header_is_plain_c(tmp_path):
 def test_defaults_and_status_strings(built_lib):
     from irotavg_b200 import _lib
     lib = _lib.load()
-    assert lib.ira_abi_version() == 1
+    assert lib.ira_abi_version() == 2
     o = _lib.Options()
     assert lib.ira_options_default(C.byref(o)) == 0
     assert o.device == -1 and o.world_size == 1 and o.cg_rtol > 0 and o.cg_max_iters > 0

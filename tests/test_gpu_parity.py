@@ -265,12 +265,12 @@ def test_large_angle_identity_start(solver):
     assert O.geodesic_rms(Q, ref.Q, g.f) <= RMS_TOL
 
 
-@pytest.mark.parametrize("solver_kind", [1, 2, 6, 8, 12, 16])
+@pytest.mark.parametrize("solver_kind", [1, 2, 6, 8, 12, 32])
 @pytest.mark.parametrize("maker", ["random", "kitti", "tiny"])
 def test_solver_variants(built_lib, solver_kind, maker):
     """solver 1 = one kernel per CG step (SELL SpMV, host-polled), 2 = persistent cooperative PCG
-    (register-resident state when one row per lane fits; the matrix in shared memory, ira_pcg2.cuh, unless 16 is
-    added), 6 = persistent with HBM-resident vectors, 8 / 12 = the
+    (register-resident state when one row per lane fits), 32 = the same with the matrix in shared memory
+    (ira_pcg2.cuh), 6 = persistent with HBM-resident vectors, 8 / 12 = the
     barrier-free kernels of the multi-GPU path (self-validating data, ira_peer.cuh) on ONE GPU, register- /
     HBM-resident."""
     import irotavg_b200 as ira
