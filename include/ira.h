@@ -73,6 +73,7 @@ typedef struct ira_options {
                               lane would let them live in registers (A/B measurement);
                               +8 = one GPU only: the barrier-free kernel of the multi-GPU path
                               (self-validating data instead of grid barriers; measured slower, kept for A/B);
+                              +64 = deal the SELL slices to the blocks round-robin instead of balanced by entries (A/B);
                               +32 = the matrix-in-shared-memory kernel (ira_pcg2.cuh; measured SLOWER: it leaves the SM
                               28 KB of L1 and the gathers lose their memory-level parallelism; kept for A/B)   */
   int32_t spmv_variant;    /* experiment knob: gather flavour / unroll of the SELL SpMV (0 = default)  */

@@ -116,6 +116,8 @@ struct ira_context {
   int res_blocks_per_sm = 0;
   // matrix-in-shared-memory PCG (ira_pcg2.cuh): cached entry columns per slice, entries per block, usable flag
   std::vector<int> h_slice_width;
+  DevBuf slice_map;          // balanced slice -> (block, warp) map of k_pcg_persistent_reg (PcgRegParams::slice_map)
+  bool slice_map_ok = false;
   int pcg2_wcap = 0, pcg2_entries = 0;
   bool pcg2_ok = false;
   DevBuf ctl, partials, bad, flush;
@@ -502,6 +504,7 @@ ira_status solve_pcg_persistent(ira_context* h) {
     PcgRegParams pr;
     pr.base = pp;
     pr.RS0r = h->R.as<double4>(); pr.RS0s = h->S.as<double4>(); pr.RS1r = h->R2.as<double4>(); pr.RS1s = h->S2.as<double4>();
+    pr.slice_map = nullptr;
     void* rargs[] = {(void*)&pr};
     const int g2 = std::max(1, cdiv(h->nslices, kMwGroups));
     IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_pcg_persistent_reg_mw, dim3(g2), dim3(kPcgThreads), rargs, 0, h->stream));
@@ -514,6 +517,7 @@ ira_status solve_pcg_persistent(ira_context* h) {
     Pcg2Params p2;
     p2.reg.base = pp;
     p2.reg.RS0r = h->R.as<double4>(); p2.reg.RS0s = h->S.as<double4>(); p2.reg.RS1r = h->R2.as<double4>(); p2.reg.RS1s = h->S2.as<double4>();
+    p2.reg.slice_map = nullptr;
     p2.wcap = h->pcg2_wcap; p2.smem_entries = h->pcg2_entries;
     void* rargs[] = {(void*)&p2};
     IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_pcg_smem, dim3(std::min(h->nslices, h->sms)), dim3(kPcg2Threads), rargs,
@@ -526,6 +530,7 @@ ira_status solve_pcg_persistent(ira_context* h) {
     PcgRegParams pr;
     pr.base = pp;
     pr.RS0r = h->R.as<double4>(); pr.RS0s = h->S.as<double4>(); pr.RS1r = h->R2.as<double4>(); pr.RS1s = h->S2.as<double4>();
+    pr.slice_map = h->slice_map_ok ? h->slice_map.as<int>() : nullptr;
     void* rargs[] = {(void*)&pr};
     switch (h->opt.spmv_variant) {
       case 1: fn = (void*)k_pcg_persistent_reg<1, 4>; break;
@@ -822,6 +827,47 @@ ira_status build_sell(ira_context* h) {
   return launch_check(h, "k_sell_inverse");
 }
 
+// Balanced deal of the SELL slices to the blocks of the register-resident PCG kernel (one slice per warp, kPcgThreads / 32
+// warps per block, one block per SM): longest-processing-time first - slices by decreasing width, each to the block
+// that holds the fewest entries so far and still has a free warp.
+ira_status plan_slice_map(ira_context* h) {
+  h->slice_map_ok = false;
+  const int wpb = kPcgThreads / 32;
+  const int grid = std::max(1, std::min(h->nslices, h->sms * std::max(1, h->pcg_blocks_per_sm)));
+  if (h->pcg_blocks_per_sm <= 0 || h->nslices <= 0 || (int64_t)grid * wpb < h->nslices || h->nslices <= h->sms * kMwGroups) return IRA_OK;
+  h->h_slice_width.resize((size_t)h->nslices);
+  IRA_CUDA(h, cudaMemcpyAsync(h->h_slice_width.data(), h->slice_width.p, sizeof(int) * (size_t)h->nslices,
+                              cudaMemcpyDeviceToHost, h->stream));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  std::vector<int> order((size_t)h->nslices);
+  for (int s = 0; s < h->nslices; ++s) order[(size_t)s] = s;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->h_slice_width[(size_t)a] > h->h_slice_width[(size_t)b]; });
+  std::vector<int64_t> load((size_t)grid, 0);
+  std::vector<int> used((size_t)grid, 0);
+  std::vector<int> map((size_t)grid * wpb, -1);
+  // (load, block) min-heap; ties broken by block index: deterministic
+  typedef std::pair<int64_t, int> Item;
+  std::vector<Item> heap;
+  for (int b = 0; b < grid; ++b) heap.push_back(Item(0, b));
+  auto cmp = [](const Item& a, const Item& b) { return a > b; };
+  std::make_heap(heap.begin(), heap.end(), cmp);
+  for (int s : order) {
+    std::pop_heap(heap.begin(), heap.end(), cmp);
+    Item it = heap.back();
+    heap.pop_back();
+    const int b = it.second;
+    map[(size_t)b * wpb + used[(size_t)b]] = s;
+    used[(size_t)b] += 1;
+    load[(size_t)b] += std::max(h->h_slice_width[(size_t)s], 1);
+    if (used[(size_t)b] < wpb) { heap.push_back(Item(load[(size_t)b], b)); std::push_heap(heap.begin(), heap.end(), cmp); }
+  }
+  IRA_CUDA(h, h->slice_map.reserve(sizeof(int) * map.size()));
+  IRA_CUDA(h, cudaMemcpyAsync(h->slice_map.p, map.data(), sizeof(int) * map.size(), cudaMemcpyHostToDevice, h->stream));
+  IRA_CUDA(h, cudaStreamSynchronize(h->stream));      // `map` is a local
+  h->slice_map_ok = true;
+  return IRA_OK;
+}
+
 // Plan of the matrix-in-shared-memory PCG kernel (ira_pcg2.cuh): one block per SM, slice s -> block s % grid,
 // warp s / grid.  Picks the largest number of entry columns per slice (`wcap`, a multiple of 4) whose (col, w2)
 // pairs fit every block's shared memory; slices wider than that read their tail from global memory.
@@ -1002,7 +1048,7 @@ ira_status ira_destroy(ira_handle h) {
                     &h->R2, &h->S2, &h->pdU, &h->pdAX, &h->pdL1, &h->pdL2, &h->pdADX, &h->pdDU, &h->pdDL1, &h->pdDL2, &h->pdEV,
                     &h->pdSIGX, &h->sell_w3, &h->pdX, &h->pdATV, &h->pdATDV, &h->pdW1P, &h->pdDX, &h->diag3, &h->dinv3,
                     &h->pdctl, &h->pdtrial, &h->mst_label, &h->mst_label2, &h->mst_order, &h->mst_order2, &h->mst_done,
-                    &h->mst_ctl, &h->mst_T0, &h->mst_T1, &h->sell_pos, &h->ipc_stage, &h->sell_colpos, &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs, &h->mate2, &h->pc3, &h->att_key})
+                    &h->mst_ctl, &h->mst_T0, &h->mst_T1, &h->slice_map, &h->sell_pos, &h->ipc_stage, &h->sell_colpos, &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs, &h->mate2, &h->pc3, &h->att_key})
     b->release();
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -1045,7 +1091,9 @@ ira_status ira_problem_upload(ira_handle h, int64_t m, int64_t n_total, int32_t 
                   n_total < (int64_t)h->opt.peer_min_rows && !h->fmt_csr && h->pcg_blocks_per_sm > 0;
   const bool one_gpu = h->opt.world_size <= 1 || h->replicated;
   h->pcg2_ok = false;
+  h->slice_map_ok = false;
   if (!h->fmt_csr && one_gpu && (h->opt.solver & 32)) IRA_TRY(plan_pcg2(h));
+  if (!h->fmt_csr && one_gpu && !(h->opt.solver & 64)) IRA_TRY(plan_slice_map(h));   // +64: round-robin deal (A/B)
   h->persistent = !h->fmt_csr && one_gpu && ((h->opt.solver & 3) != 1 || h->replicated) && h->pcg_blocks_per_sm > 0;
   h->peer = false;
   if ((h->opt.world_size > 1 && !h->replicated && (h->opt.shard_mode == 1 || h->opt.shard_mode == 2)) ||

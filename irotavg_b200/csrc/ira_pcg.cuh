@@ -680,6 +680,11 @@ k_pcg_persistent(const PcgParams p) {
 struct PcgRegParams {
   PcgParams base;
   double4* RS0r; double4* RS0s; double4* RS1r; double4* RS1s;   // ping-pong (r, s) of paired rows
+  // slice of (block, warp), -1 = none: slices dealt to blocks so that every SM gathers the same number of entries
+  // (null: round-robin, slice = block + grid * warp).  Degree-sorted 1024-row windows make slice widths periodic
+  // (period 32 slices); round-robin over 148 blocks aliases with that period and leaves the heaviest block 14 %
+  // above the mean - and every grid barrier waits for the heaviest block.
+  const int* slice_map;
 };
 
 template <int V, int UNR>
@@ -692,11 +697,12 @@ k_pcg_persistent_reg(const PcgRegParams q) {
   __shared__ double sc_bb[3], sc_go[3], sc_ao[3], sc_a[3], sc_b[3], sc_rr[3];
   __shared__ int sc_stop;
   const int lane = threadIdx.x & 31;
-  const int slice = blockIdx.x + gridDim.x * (threadIdx.x >> 5);     // <= 1 slice per warp
+  const int slice = q.slice_map ? q.slice_map[blockIdx.x * (kPcgThreads / 32) + (threadIdx.x >> 5)]
+                                : (int)(blockIdx.x + gridDim.x * (threadIdx.x >> 5));     // <= 1 slice per warp
   const bool has_pairs = p.npairs != nullptr && *p.npairs > 0;
   int row = -1, width = 0, mt = -1, mt2 = -1;
   int64_t base = 0;
-  if (slice < p.nslices) {
+  if (slice >= 0 && slice < p.nslices) {
     row = p.sell_row[slice * kSellC + lane];
     width = p.slice_width[slice];
     base = (int64_t)p.slice_off[slice] + lane;

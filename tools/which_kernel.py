@@ -4,7 +4,7 @@ import numpy as np
 import irotavg_b200 as ira
 from oracle import graphs as G
 g = G.random_graph()
-for sv in (0, 32):
+for sv in (0, 64, 32):      # default (balanced slice deal), round-robin deal, matrix in shared memory
     with ira.Solver(solver=sv) as s:
         s.upload(g.QQ, g.I, g.Q0, g.f)
         info = s.irls_resident(1, 5*np.pi/180, 30, -1.0)
