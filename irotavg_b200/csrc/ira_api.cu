@@ -27,6 +27,7 @@
 #include "ira_l1ra.cuh"
 #include "ira_mst.cuh"
 #include "ira_small.cuh"
+#include "ira_coarse.cuh"
 #include "ira_peer.cuh"
 
 using namespace ira;
@@ -116,6 +117,11 @@ struct ira_context {
   int res_blocks_per_sm = 0;
   // matrix-in-shared-memory PCG (ira_pcg2.cuh): cached entry columns per slice, entries per block, usable flag
   std::vector<int> h_slice_width;
+  // two-level PCG for small / medium graphs (ira_coarse.cuh)
+  DevBuf coarse_AC, coarse_RC;
+  bool coarse_ok = false;
+  int coarse_nc = 0, coarse_bsz = 0, coarse_smem = 0;
+  int cur_cost = -1;         // cost of the running irls call (the L1 family keeps the block-Jacobi kernels)
   DevBuf slice_map;          // balanced slice -> (block, warp) map of k_pcg_persistent_reg (PcgRegParams::slice_map)
   bool slice_map_ok = false;
   int pcg2_wcap = 0, pcg2_entries = 0;
@@ -474,8 +480,22 @@ ira_status run_pairing(ira_context* h) {
   return IRA_OK;
 }
 
+ira_status l1ra_alloc(ira_context* h);
+ira_status launch_pcg_coarse(ira_context* h, const double4* rhs, double4* xout);
+
 ira_status solve_pcg_persistent(ira_context* h) {
   IRA_TRY(run_rhs(h));
+  // small / medium graphs, bounded robust weights (everything but the L1 family, whose stiff pairs need the exact
+  // 2x2 / 3x3 blocks): Jacobi + coarse space, the same weights for the three coordinates
+  if (h->coarse_ok && !(h->opt.solver & 4) && h->opt.spmv_variant == 0 && h->cur_cost != (int)kL1 && h->cur_cost != (int)kL15 &&
+      h->cur_cost != (int)kL05) {
+    IRA_TRY(l1ra_alloc(h));
+    ProfScope ps(h, KC_PCG);
+    k_w2_to_w3<<<grid_nodes(h, (int)std::min<int64_t>(std::max<int64_t>(h->sell_total, h->n), 1 << 30)), 256, 0, h->stream>>>(
+        h->sell_w2.as<double>(), h->diag.as<double>(), h->sell_total, h->n, h->sell_w3.as<double4>(), h->diag3.as<double4>());
+    IRA_TRY(launch_check(h, "k_w2_to_w3"));
+    return launch_pcg_coarse(h, h->B.as<double4>(), h->X.as<double4>());
+  }
   const bool pairing = h->opt.pair_theta > 0.0;
   if (pairing) IRA_TRY(run_pairing(h));
   PcgParams pp;
@@ -868,6 +888,53 @@ ira_status plan_slice_map(ira_context* h) {
   return IRA_OK;
 }
 
+// Two-level PCG (ira_coarse.cuh) for graphs of up to kCoarseMaxRows nodes: partition of the node indices into
+// nc <= 64 contiguous blocks; shared memory for the three nc x nc inverses.
+ira_status plan_coarse(ira_context* h) {
+  h->coarse_ok = false;
+  const int n = h->n, nfree = h->n - h->f;
+  if (h->pcg_blocks_per_sm <= 0 || h->nslices <= 0 || n > kCoarseMaxRows || nfree < 128) return IRA_OK;
+  const int bsz = std::max(2, cdiv(n, kCoarseMax));
+  const int nc = cdiv(n, bsz);
+  if (nc < 2 || nc > kCoarseMax) return IRA_OK;
+  const int bytes = (int)sizeof(double) * (3 * nc * nc + 8 * nc);
+  if (cudaFuncSetAttribute(k_pcg_coarse_w3, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) { cudaGetLastError(); return IRA_OK; }
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_coarse_w3, kCoarseThreads, (size_t)bytes) != cudaSuccess || nb < 1) {
+    cudaGetLastError();
+    return IRA_OK;
+  }
+  IRA_CUDA(h, h->coarse_AC.reserve(sizeof(double) * 3 * (size_t)nc * nc));
+  IRA_CUDA(h, h->coarse_RC.reserve(sizeof(double4) * (size_t)nc));
+  h->coarse_nc = nc; h->coarse_bsz = bsz; h->coarse_smem = bytes;
+  h->coarse_ok = true;
+  return IRA_OK;
+}
+
+// One linear solve with three weight sets by the two-level kernel: (sell_w3, diag3) x = rhs.
+ira_status launch_pcg_coarse(ira_context* h, const double4* rhs, double4* xout) {
+  PcgCoarseParams q;
+  PcgW3Params& pp = q.w;
+  pp.n = h->n; pp.nslices = h->nslices; pp.max_iters = std::max(0, h->opt.cg_max_iters);
+  pp.rtol2 = h->opt.cg_rtol * h->opt.cg_rtol;
+  pp.sell_row = h->sell_row.as<int>(); pp.slice_off = h->slice_off.as<int>(); pp.slice_width = h->slice_width.as<int>();
+  pp.sell_col = h->sell_col.as<int>(); pp.sell_w3 = h->sell_w3.as<double4>(); pp.diag3 = h->diag3.as<double4>();
+  pp.B = rhs;
+  pp.X = xout; pp.R = h->R.as<double4>(); pp.U = h->Z.as<double4>(); pp.W = h->AP.as<double4>();
+  pp.P = h->P.as<double4>(); pp.S = h->S.as<double4>(); pp.DINV = h->dinv3.as<double4>();
+  pp.partials = h->partials.as<double>(); pp.ctl = h->ctl.as<Ctl>();
+  q.sell_pos = h->sell_pos.as<int>();
+  q.f = h->f; q.nc = h->coarse_nc; q.bsz = h->coarse_bsz;
+  q.AC = h->coarse_AC.as<double>(); q.RC = h->coarse_RC.as<double4>();
+  const int grid = std::max(1, std::min(h->nslices, h->sms));
+  void* args[] = {(void*)&q};
+  IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_pcg_coarse_w3, dim3(grid), dim3(kCoarseThreads), args,
+                                          (size_t)h->coarse_smem, h->stream));
+  h->launches++;
+  h->pcg_kernel = 7;
+  return IRA_OK;
+}
+
 // Plan of the matrix-in-shared-memory PCG kernel (ira_pcg2.cuh): one block per SM, slice s -> block s % grid,
 // warp s / grid.  Picks the largest number of entry columns per slice (`wcap`, a multiple of 4) whose (col, w2)
 // pairs fit every block's shared memory; slices wider than that read their tail from global memory.
@@ -1048,7 +1115,7 @@ ira_status ira_destroy(ira_handle h) {
                     &h->R2, &h->S2, &h->pdU, &h->pdAX, &h->pdL1, &h->pdL2, &h->pdADX, &h->pdDU, &h->pdDL1, &h->pdDL2, &h->pdEV,
                     &h->pdSIGX, &h->sell_w3, &h->pdX, &h->pdATV, &h->pdATDV, &h->pdW1P, &h->pdDX, &h->diag3, &h->dinv3,
                     &h->pdctl, &h->pdtrial, &h->mst_label, &h->mst_label2, &h->mst_order, &h->mst_order2, &h->mst_done,
-                    &h->mst_ctl, &h->mst_T0, &h->mst_T1, &h->slice_map, &h->sell_pos, &h->ipc_stage, &h->sell_colpos, &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs, &h->mate2, &h->pc3, &h->att_key})
+                    &h->mst_ctl, &h->mst_T0, &h->mst_T1, &h->slice_map, &h->coarse_AC, &h->coarse_RC, &h->sell_pos, &h->ipc_stage, &h->sell_colpos, &h->pair_key, &h->pair_key2, &h->pair_w2, &h->mate, &h->pc1, &h->pc2, &h->npairs, &h->mate2, &h->pc3, &h->att_key})
     b->release();
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -1094,6 +1161,8 @@ ira_status ira_problem_upload(ira_handle h, int64_t m, int64_t n_total, int32_t 
   h->slice_map_ok = false;
   if (!h->fmt_csr && one_gpu && (h->opt.solver & 32)) IRA_TRY(plan_pcg2(h));
   if (!h->fmt_csr && one_gpu && !(h->opt.solver & 64)) IRA_TRY(plan_slice_map(h));   // +64: round-robin deal (A/B)
+  h->coarse_ok = false;
+  if (!h->fmt_csr && one_gpu && !(h->opt.solver & 128)) IRA_TRY(plan_coarse(h));       // +128: one-level kernels only (A/B)
   h->persistent = !h->fmt_csr && one_gpu && ((h->opt.solver & 3) != 1 || h->replicated) && h->pcg_blocks_per_sm > 0;
   h->peer = false;
   if ((h->opt.world_size > 1 && !h->replicated && (h->opt.shard_mode == 1 || h->opt.shard_mode == 2)) ||
@@ -1147,6 +1216,7 @@ ira_status ira_irls_resident(ira_handle h, int32_t cost, double sigma, int32_t m
   double score = std::numeric_limits<double>::max();                      // :574
   int iters = 0;
   ira_status rc = IRA_OK;
+  h->cur_cost = cost;
   while (score > change_th && iters < max_iters) {                         // :590
     IRA_TRY(run_residual(h, h->Q.as<double4>(), 0));                       // :592-593
     int cg_it = 0, hit = 0;
@@ -1494,7 +1564,9 @@ ira_status l1decode_pd_device(ira_context* h, int pdmaxiter, int* newton_cg_iter
                                                            h->pdSIGX.as<double4>(), h->sell_w3.as<double4>(),
                                                            h->diag3.as<double4>(), h->nslices);
     IRA_TRY(launch_check(h, "k_sell_hweights"));
-    {                                                                 // H dx = w1p  (:319)
+    if (h->coarse_ok) {                                               // H dx = w1p  (:319), two-level PCG
+      IRA_TRY(launch_pcg_coarse(h, h->pdW1P.as<double4>(), h->pdDX.as<double4>()));
+    } else {                                                          // H dx = w1p  (:319)
       PcgW3Params pp;
       pp.n = n; pp.nslices = h->nslices; pp.max_iters = std::max(0, h->opt.cg_max_iters);
       pp.rtol2 = h->opt.cg_rtol * h->opt.cg_rtol;
