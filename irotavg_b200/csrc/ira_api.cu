@@ -890,14 +890,24 @@ ira_status plan_slice_map(ira_context* h) {
 
 // Two-level PCG (ira_coarse.cuh) for graphs of up to kCoarseMaxRows nodes: partition of the node indices into
 // nc <= 64 contiguous blocks; shared memory for the three nc x nc inverses.
-ira_status plan_coarse(ira_context* h) {
+ira_status plan_coarse(ira_context* h, const int32_t* I_pairs) {
   h->coarse_ok = false;
   const int n = h->n, nfree = h->n - h->f;
   if (h->pcg_blocks_per_sm <= 0 || h->nslices <= 0 || n > kCoarseMaxRows || nfree < 128) return IRA_OK;
   const int bsz = std::max(2, cdiv(n, kCoarseMax));
   const int nc = cdiv(n, bsz);
   if (nc < 2 || nc > kCoarseMax) return IRA_OK;
-  const int bytes = (int)sizeof(double) * (3 * nc * nc + 8 * nc);
+  // Is the graph a chain in its node numbering?  Long-range edges (loop closures) make a view graph an expander:
+  // config 2's 9 % of them leave one-level PCG at 64 iterations per solve and the two-level kernel, at 2.5x the cost
+  // per iteration, loses (measured 19.7 against 9.9 ms); a SLAM stream (0.05 %) or the reference's fixture (none) needs
+  // thousands of iterations without the coarse space.  Threshold: at most 2 % of the edges span more than two blocks.
+  int64_t far = 0;
+  for (int64_t k = 0; k < h->m; ++k) {
+    const int64_t d = (int64_t)I_pairs[2 * k] - (int64_t)I_pairs[2 * k + 1];
+    if ((d < 0 ? -d : d) > 2 * (int64_t)bsz) ++far;
+  }
+  if (far * 50 > h->m) return IRA_OK;
+  const int bytes = (int)sizeof(double) * (((3 * nc * nc + 3) & ~3) + 8 * nc);
   if (cudaFuncSetAttribute(k_pcg_coarse_w3, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) { cudaGetLastError(); return IRA_OK; }
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_coarse_w3, kCoarseThreads, (size_t)bytes) != cudaSuccess || nb < 1) {
@@ -1162,7 +1172,7 @@ ira_status ira_problem_upload(ira_handle h, int64_t m, int64_t n_total, int32_t 
   if (!h->fmt_csr && one_gpu && (h->opt.solver & 32)) IRA_TRY(plan_pcg2(h));
   if (!h->fmt_csr && one_gpu && !(h->opt.solver & 64)) IRA_TRY(plan_slice_map(h));   // +64: round-robin deal (A/B)
   h->coarse_ok = false;
-  if (!h->fmt_csr && one_gpu && !(h->opt.solver & 128)) IRA_TRY(plan_coarse(h));       // +128: one-level kernels only (A/B)
+  if (!h->fmt_csr && one_gpu && !(h->opt.solver & 128)) IRA_TRY(plan_coarse(h, I_pairs));   // +128: one-level kernels only (A/B)
   h->persistent = !h->fmt_csr && one_gpu && ((h->opt.solver & 3) != 1 || h->replicated) && h->pcg_blocks_per_sm > 0;
   h->peer = false;
   if ((h->opt.world_size > 1 && !h->replicated && (h->opt.shard_mode == 1 || h->opt.shard_mode == 2)) ||

@@ -31,7 +31,7 @@
 namespace ira {
 
 constexpr int kCoarseMax = 64;          // coarse unknowns per coordinate (3 x 64 x 64 doubles = 96 KB of shared memory)
-constexpr int kCoarseThreads = 256;
+constexpr int kCoarseThreads = 384;     // >= kPcgNV warps: pcg_grid_reduce gives each of its 9 sums to one warp
 constexpr int kCoarseMaxRows = 32768;   // larger graphs keep the one-level kernels
 
 struct PcgCoarseParams {
@@ -105,9 +105,9 @@ __global__ void __launch_bounds__(kCoarseThreads, 1)
 k_pcg_coarse_w3(const PcgCoarseParams q) {
   const PcgW3Params& p = q.w;
   cg::grid_group grid = cg::this_grid();
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  extern __shared__ __align__(32) unsigned char dyn_smem[];
   double* const ainv = reinterpret_cast<double*>(dyn_smem);                       // [3][nc][nc]
-  double4* const yc = reinterpret_cast<double4*>(ainv + 3 * q.nc * q.nc);         // [nc]
+  double4* const yc = reinterpret_cast<double4*>(ainv + ((3 * q.nc * q.nc + 3) & ~3));   // [nc], 32-byte aligned
   double4* const rc_s = yc + q.nc;                                                // [nc]
   __shared__ double red[kPcgNV * 32];
   __shared__ double tot[kPcgNV];

@@ -458,6 +458,7 @@ constexpr int kPcgNV = 9;
 
 // Block-ordered grid reduction through one grid barrier; every thread of every block returns the
 // same totals (bitwise), so loop control and alpha/beta stay uniform without a broadcast.
+// Needs at least kPcgNV warps per block (warp k reduces sum k).
 __device__ __forceinline__ void pcg_grid_reduce(double (&v)[kPcgNV], double* partials, cg::grid_group& grid,
                                                 double* red /* [kPcgNV*32] */, double* tot /* [kPcgNV] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
