@@ -128,6 +128,7 @@ struct ira_context {
   bool pcg2_ok = false;
   DevBuf ctl, partials, bad, flush;
   Ctl* h_ctl = nullptr;  // pinned
+  Ctl* h_hist = nullptr; // pinned, IRA_STATS_MAX_ITERS records: per-iteration control blocks of a call that never tests the score
 
   // comm
   ncclComm_t comm = nullptr;
@@ -191,8 +192,8 @@ struct EventPair {
 
 cudaEvent_t prof_event(ira_context* h) {
   if (h->ev_used == h->ev_pool.size()) {
-    cudaEvent_t e;
-    cudaEventCreate(&e);
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return nullptr; }   // profiling is best effort
     h->ev_pool.push_back(e);
   }
   return h->ev_pool[h->ev_used++];
@@ -215,9 +216,11 @@ struct ProfScope {
     if (h->opt.profile) {
       if (h->spans.size() >= 8192) prof_flush(h);
       ira_context::Span s{cls, prof_event(h), prof_event(h)};
-      cudaEventRecord(s.a, h->stream);
-      h->spans.push_back(s);
-      idx = (int)h->spans.size() - 1;
+      if (s.a && s.b) {
+        cudaEventRecord(s.a, h->stream);
+        h->spans.push_back(s);
+        idx = (int)h->spans.size() - 1;
+      }
     }
   }
   ~ProfScope() { if (idx >= 0) cudaEventRecord(h->spans[idx].b, h->stream); }
@@ -936,7 +939,9 @@ ira_status launch_pcg_coarse(ira_context* h, const double4* rhs, double4* xout) 
   q.sell_pos = h->sell_pos.as<int>();
   q.f = h->f; q.nc = h->coarse_nc; q.bsz = h->coarse_bsz;
   q.AC = h->coarse_AC.as<double>(); q.RC = h->coarse_RC.as<double4>();
-  const int grid = std::max(1, std::min(h->nslices, h->sms));
+  // about 8 slices per block (12 warps): few blocks keep the four grid barriers of an iteration cheap, yet leave
+  // at least one warp per block of the partition for the restriction
+  const int grid = std::max(1, std::min(h->sms, std::max(cdiv(h->nslices, 8), std::min(h->nslices, cdiv(h->coarse_nc, kCoarseThreads / 32)))));
   void* args[] = {(void*)&q};
   IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_pcg_coarse_w3, dim3(grid), dim3(kCoarseThreads), args,
                                           (size_t)h->coarse_smem, h->stream));
@@ -1098,6 +1103,7 @@ ira_status ira_create(ira_handle* out, const ira_options* opt) {
   h->sms = prop.multiProcessorCount;
   bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaMallocHost((void**)&h->h_ctl, sizeof(Ctl)) == cudaSuccess;
+  ok = ok && cudaMallocHost((void**)&h->h_hist, sizeof(Ctl) * IRA_STATS_MAX_ITERS) == cudaSuccess;
   ok = ok && h->ctl.reserve(sizeof(Ctl)) == cudaSuccess;
   ok = ok && h->partials.reserve(sizeof(double) * 8 * kRedMaxBlocks) == cudaSuccess;
   ok = ok && h->bad.reserve(sizeof(int)) == cudaSuccess;
@@ -1129,6 +1135,7 @@ ira_status ira_destroy(ira_handle h) {
     b->release();
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->h_hist) cudaFreeHost(h->h_hist);
   if (h->h_pdctl) cudaFreeHost(h->h_pdctl);
   if (h->small_in) cudaFreeHost(h->small_in);
   if (h->small_out) cudaFreeHost(h->small_out);
@@ -1227,6 +1234,26 @@ ira_status ira_irls_resident(ira_handle h, int32_t cost, double sigma, int32_t m
   int iters = 0;
   ira_status rc = IRA_OK;
   h->cur_cost = cost;
+  const bool deferred = change_th < 0.0 && h->persistent && !h->peer && max_iters <= IRA_STATS_MAX_ITERS;
+  // one iteration's record -> stats (cg_it / rel / hit come from the control block on the persistent paths)
+  auto record = [&](const Ctl& c, int k, int cg_it, double rel, int hit) {
+    if (h->persistent || h->peer) {
+      cg_it = c.cg_iters;
+      bool conv = true;
+      rel = 0.0;
+      for (int q = 0; q < 3; ++q) {
+        if (c.bnorm2[q] > 0.0) rel = std::max(rel, sqrt(c.rnorm2[q] / c.bnorm2[q]));
+        if (!(c.rnorm2[q] <= c.rtol2 * c.bnorm2[q])) conv = false;
+      }
+      hit = conv ? 0 : 1;
+    }
+    if (stats && k < IRA_STATS_MAX_ITERS) {
+      stats->score[k] = c.score;
+      stats->cg_iters[k] = cg_it;
+      stats->cg_relres[k] = rel;
+    }
+    if (stats) { stats->cg_iters_total += cg_it; stats->cg_hit_max += hit; }
+  };
   while (score > change_th && iters < max_iters) {                         // :590
     IRA_TRY(run_residual(h, h->Q.as<double4>(), 0));                       // :592-593
     int cg_it = 0, hit = 0;
@@ -1247,30 +1274,33 @@ ira_status ira_irls_resident(ira_handle h, int32_t cost, double sigma, int32_t m
           h->Q.as<double4>(), h->X.as<double4>(), n, h->f, h->ctl.as<Ctl>(), h->partials.as<double>());  // :729-737
       IRA_TRY(launch_check(h, "k_update"));
     }
+    if (deferred) {
+      // change_th < 0: the loop test (:590) can only end the loop on a NaN score, so nothing has to come back per
+      // iteration: the control block is copied out asynchronously and read after the last iteration
+      IRA_CUDA(h, cudaMemcpyAsync(&h->h_hist[iters], h->ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
+      iters++;                                                             // :739
+      continue;
+    }
     IRA_TRY(fetch_ctl(h));
-    score = h->h_ctl->score;
     if (h->peer) h->peer_epoch = h->h_ctl->epoch;
-    if (h->persistent || h->peer) {
-      const Ctl& c = *h->h_ctl;
-      cg_it = c.cg_iters;
-      bool conv = true;
-      for (int k = 0; k < 3; ++k) {
-        if (c.bnorm2[k] > 0.0) rel = std::max(rel, sqrt(c.rnorm2[k] / c.bnorm2[k]));
-        if (!(c.rnorm2[k] <= c.rtol2 * c.bnorm2[k])) conv = false;
-      }
-      hit = conv ? 0 : 1;
-    }
-    if (stats && iters < IRA_STATS_MAX_ITERS) {
-      stats->score[iters] = score;
-      stats->cg_iters[iters] = cg_it;
-      stats->cg_relres[iters] = rel;
-    }
-    if (stats) { stats->cg_iters_total += cg_it; stats->cg_hit_max += hit; }
+    record(*h->h_ctl, iters, cg_it, rel, hit);
+    score = h->h_ctl->score;
     iters++;                                                               // :739
     if (!std::isfinite(score)) { if (n - h->f > 0) rc = IRA_ERR_NONFINITE; break; }
   }
   IRA_CUDA(h, cudaEventRecord(ev1, h->stream));
   IRA_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (deferred && iters > 0) {
+    for (int k = 0; k < iters; ++k) {
+      record(h->h_hist[k], k, 0, 0.0, 0);
+      if (!std::isfinite(h->h_hist[k].score)) {          // the reference's loop ends here (NaN > th is false)
+        if (n - h->f > 0) rc = IRA_ERR_NONFINITE;
+        iters = k + 1;
+        break;
+      }
+    }
+    *h->h_ctl = h->h_hist[iters - 1];
+  }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ev0, ev1);
   prof_collect(h, stats);
