@@ -939,9 +939,9 @@ ira_status launch_pcg_coarse(ira_context* h, const double4* rhs, double4* xout) 
   q.sell_pos = h->sell_pos.as<int>();
   q.f = h->f; q.nc = h->coarse_nc; q.bsz = h->coarse_bsz;
   q.AC = h->coarse_AC.as<double>(); q.RC = h->coarse_RC.as<double4>();
-  // about 8 slices per block (12 warps): few blocks keep the four grid barriers of an iteration cheap, yet leave
-  // at least one warp per block of the partition for the restriction
-  const int grid = std::max(1, std::min(h->sms, std::max(cdiv(h->nslices, 8), std::min(h->nslices, cdiv(h->coarse_nc, kCoarseThreads / 32)))));
+  // one slice per warp, 12 warps per block: as few blocks as hold the slices (cheap grid barriers)
+  const int grid = std::max(1, cdiv(h->nslices, kCoarseThreads / 32));
+  if (grid > h->sms) { h->err = "two-level PCG: more slices than resident warps"; return IRA_ERR_INVALID_ARG; }
   void* args[] = {(void*)&q};
   IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_pcg_coarse_w3, dim3(grid), dim3(kCoarseThreads), args,
                                           (size_t)h->coarse_smem, h->stream));

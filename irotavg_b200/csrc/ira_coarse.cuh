@@ -19,12 +19,13 @@
 //   set-up   A_c = P^T L P per coordinate, nc <= 64 blocks: one warp per coarse row walks its rows' SELL entries in
 //            a fixed order (deterministic sums); every block then inverts the three nc x nc matrices in its own
 //            shared memory (in-place Gauss-Jordan, 3 x 32 KB) - identical arithmetic in every block, no broadcast;
-//   per PCG iteration (Chronopoulos-Gear, one fused reduction):
-//     A  w = L u, partial dots                                   -> grid reduction (barrier 1)
-//     B  p, s, x, r updated, r published                         -> barrier 2
+//   per PCG iteration (Chronopoulos-Gear, one fused reduction; one slice per warp, its rows' x r p s u in registers):
+//     A  w = L u (gathers of u, software pipelined), partial dots -> grid reduction (barrier 1)
+//     B  p, s, x, r updated in registers, r published            -> barrier 2
 //     C  r_c = P^T r, one warp per block of the partition        -> barrier 3
 //     D  y_c = A_c^-1 r_c from shared memory (every block, redundantly), u = D^-1 r + y_c[block(row)]   -> barrier 4
-// Four barriers instead of two per iteration (8-9 us against 5 on these small grids) for 6-13x fewer iterations.
+// Four barriers instead of two per iteration (2-3x the cost of a one-level iteration on these small grids) for 6-13x
+// fewer iterations.
 #pragma once
 #include "ira_l1ra.cuh"
 
@@ -32,7 +33,7 @@ namespace ira {
 
 constexpr int kCoarseMax = 64;          // coarse unknowns per coordinate (3 x 64 x 64 doubles = 96 KB of shared memory)
 constexpr int kCoarseThreads = 384;     // >= kPcgNV warps: pcg_grid_reduce gives each of its 9 sums to one warp
-constexpr int kCoarseMaxRows = 32768;   // larger graphs keep the one-level kernels
+constexpr int kCoarseMaxRows = 32768;   // larger graphs keep the one-level kernels (148 x 12 warps hold 56 832 rows)
 
 struct PcgCoarseParams {
   PcgW3Params w;                        // matrix (3 weights per entry), vectors, partials, ctl
@@ -42,25 +43,6 @@ struct PcgCoarseParams {
   double* AC;                           // [3][nc][nc] assembled coarse matrices (global scratch)
   double4* RC;                          // [nc] coarse residual of the current iteration
 };
-
-// u = D^-1 r + P A_c^-1 P^T r for this block's rows; `yc` (shared) must hold A_c^-1 r_c.
-__device__ __forceinline__ void coarse_apply_rows(const PcgCoarseParams& q, const double4* yc, int gwarp, int nwarps, int lane) {
-  const PcgW3Params& p = q.w;
-  for (int s = gwarp; s < p.nslices; s += nwarps) {
-    const int row = p.sell_row[s * kSellC + lane];
-    if (row >= 0) {
-      const double4 r = ld256(p.R + row), di = ld256(p.DINV + row);
-      double4 u = make_double4(di.x * r.x, di.y * r.y, di.z * r.z, 0.0);
-      if (row >= q.f) {                                            // fixed rows are not unknowns: u stays 0 there
-        const double4 y = yc[row / q.bsz];
-        if (di.x != 0.0) u.x += y.x;
-        if (di.y != 0.0) u.y += y.y;
-        if (di.z != 0.0) u.z += y.z;
-      }
-      st256(p.U + row, u);
-    }
-  }
-}
 
 // r_c = P^T r: warp a sums the rows of block a in a fixed order (lane-strided partial sums, butterfly).
 __device__ __forceinline__ void coarse_restrict(const PcgCoarseParams& q, int gwarp, int nwarps, int lane) {
@@ -114,25 +96,32 @@ k_pcg_coarse_w3(const PcgCoarseParams q) {
   __shared__ double sc_bb[3], sc_go[3], sc_ao[3], sc_a[3], sc_b[3], sc_rr[3];
   __shared__ int sc_stop;
   const int lane = threadIdx.x & 31;
-  const int gwarp = blockIdx.x + gridDim.x * (threadIdx.x >> 5);
-  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int wpb = kCoarseThreads / 32;
+  const int gwarp = blockIdx.x * wpb + (threadIdx.x >> 5);           // one slice per warp for the whole solve:
+  const int nwarps = gridDim.x * wpb;                                 // the rows' x r p s u stay in registers
   const int nc = q.nc;
+  int row = -1, width = 0;
+  int64_t base = 0;
+  if (gwarp < p.nslices) {
+    row = p.sell_row[gwarp * kSellC + lane];
+    width = p.slice_width[gwarp];
+    base = (int64_t)p.slice_off[gwarp] + lane;
+  }
+  const bool in_p = row >= q.f;                                       // fixed rows are never coarse unknowns
 
   // ---- set-up 1: D^-1, x = 0, r = b; coarse matrices A_c = P^T L P, one warp per coarse row ---------------------
   double v[kPcgNV];
 #pragma unroll
   for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
-  for (int s = gwarp; s < p.nslices; s += nwarps) {
-    const int row = p.sell_row[s * kSellC + lane];
-    if (row >= 0) {
-      const double4 b = ldg256(p.B + row), d = ldg256(p.diag3 + row);
-      const double4 di = make_double4(d.x > 0.0 ? 1.0 / d.x : 0.0, d.y > 0.0 ? 1.0 / d.y : 0.0, d.z > 0.0 ? 1.0 / d.z : 0.0, 0.0);
-      st256(p.DINV + row, di);
-      const double4 z4 = make_double4(0, 0, 0, 0);
-      st256(p.X + row, z4); st256(p.P + row, z4); st256(p.S + row, z4);
-      st256(p.R + row, b);
-      v[0] += b.x * b.x; v[1] += b.y * b.y; v[2] += b.z * b.z;
-    }
+  double x0 = 0, x1 = 0, x2 = 0, r0 = 0, r1 = 0, r2 = 0, p0 = 0, p1 = 0, p2 = 0, s0 = 0, s1 = 0, s2 = 0;
+  double u0 = 0, u1 = 0, u2 = 0, d0 = 0, d1 = 0, d2 = 0;
+  if (row >= 0) {
+    const double4 b = ldg256(p.B + row), d = ldg256(p.diag3 + row);
+    d0 = d.x > 0.0 ? 1.0 / d.x : 0.0; d1 = d.y > 0.0 ? 1.0 / d.y : 0.0; d2 = d.z > 0.0 ? 1.0 / d.z : 0.0;
+    st256(p.DINV + row, make_double4(d0, d1, d2, 0.0));
+    r0 = b.x; r1 = b.y; r2 = b.z;
+    st256(p.R + row, b);
+    v[0] = r0 * r0; v[1] = r1 * r1; v[2] = r2 * r2;
   }
   for (int a = gwarp; a < nc; a += nwarps) {
     // lane l owns the coarse columns l and l + 32; every entry of every row of block a is visited in a fixed order
@@ -141,14 +130,14 @@ k_pcg_coarse_w3(const PcgCoarseParams q) {
     for (int vv = v0; vv < v1; ++vv) {
       const int pos = q.sell_pos[vv];
       const int sl = pos / kSellC, ln = pos % kSellC;
-      const int width = p.slice_width[sl];
-      const int64_t base = (int64_t)p.slice_off[sl] + ln;
-      for (int j0 = 0; j0 < width; j0 += 32) {                       // 32 entries of the row at a time, one per lane
+      const int wd = p.slice_width[sl];
+      const int64_t bs = (int64_t)p.slice_off[sl] + ln;
+      for (int j0 = 0; j0 < wd; j0 += 32) {                         // 32 entries of the row at a time, one per lane
         const int j = j0 + lane;
         int col = vv;
         double4 w3 = make_double4(0, 0, 0, 0);
-        if (j < width) { col = __ldg(p.sell_col + base + (int64_t)j * kSellC); w3 = ldg256(p.sell_w3 + base + (int64_t)j * kSellC); }
-        const int cnt = min(32, width - j0);
+        if (j < wd) { col = __ldg(p.sell_col + bs + (int64_t)j * kSellC); w3 = ldg256(p.sell_w3 + bs + (int64_t)j * kSellC); }
+        const int cnt = min(32, wd - j0);
         for (int e = 0; e < cnt; ++e) {                              // then added one after the other by the column's owner
           const int ce = __shfl_sync(0xffffffffu, col, e);
           const double wx = __shfl_sync(0xffffffffu, w3.x, e), wy = __shfl_sync(0xffffffffu, w3.y, e), wz = __shfl_sync(0xffffffffu, w3.z, e);
@@ -237,61 +226,71 @@ k_pcg_coarse_w3(const PcgCoarseParams q) {
   coarse_restrict(q, gwarp, nwarps, lane);
   grid.sync();
   coarse_solve(q, ainv, yc, rc_s);
-  coarse_apply_rows(q, yc, gwarp, nwarps, lane);
+  if (row >= 0) {
+    u0 = d0 * r0; u1 = d1 * r1; u2 = d2 * r2;
+    if (in_p) {
+      const double4 y = yc[row / q.bsz];
+      if (d0 != 0.0) u0 += y.x;
+      if (d1 != 0.0) u1 += y.y;
+      if (d2 != 0.0) u2 += y.z;
+    }
+    st256(p.U + row, make_double4(u0, u1, u2, 0.0));
+  }
   grid.sync();
 
   int it = 0;
   while (!sc_stop) {
-    // ---- A: w = L u, gamma = r.u, delta = u.w, |r|^2 ---------------------------------------------------------------
+    // ---- A: w = L u (software pipelined: the (col, w3) of batch k + 1 are requested before batch k's gathers are
+    //      consumed), gamma = r.u, delta = u.w, |r|^2 --------------------------------------------------------------
+    double w0 = 0, w1 = 0, w2 = 0;
+    if (width > 0) {
+      int c[4]; double4 w3[4];
 #pragma unroll
-    for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
-    for (int s = gwarp; s < p.nslices; s += nwarps) {
-      const int row = p.sell_row[s * kSellC + lane];
-      const int width = p.slice_width[s];
-      const int64_t base = (int64_t)p.slice_off[s] + lane;
-      const double4 u = row >= 0 ? ld256(p.U + row) : make_double4(0, 0, 0, 0);
-      double ax = 0, ay = 0, az = 0;
+      for (int t = 0; t < 4; ++t) {
+        const int64_t o = base + (int64_t)t * kSellC;
+        c[t] = __ldg(p.sell_col + o); w3[t] = ldg256(p.sell_w3 + o);
+      }
       for (int j = 0; j < width; j += 4) {                              // widths are multiples of 4
-        int c[4]; double4 w3[4], uc[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int64_t o = base + (int64_t)(j + t) * kSellC;
-          c[t] = __ldg(p.sell_col + o);
-          w3[t] = ldg256(p.sell_w3 + o);
-        }
+        double4 uc[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) uc[t] = ld256(p.U + c[t]);
+        int cn[4] = {0, 0, 0, 0}; double4 wn[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) wn[t] = make_double4(0, 0, 0, 0);
+        if (j + 4 < width) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int64_t o = base + (int64_t)(j + 4 + t) * kSellC;
+            cn[t] = __ldg(p.sell_col + o); wn[t] = ldg256(p.sell_w3 + o);
+          }
+        }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          ax += w3[t].x * (u.x - uc[t].x); ay += w3[t].y * (u.y - uc[t].y); az += w3[t].z * (u.z - uc[t].z);
+          w0 += w3[t].x * (u0 - uc[t].x); w1 += w3[t].y * (u1 - uc[t].y); w2 += w3[t].z * (u2 - uc[t].z);
         }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { c[t] = cn[t]; w3[t] = wn[t]; }
       }
-      if (row >= 0) {
-        st256(p.W + row, make_double4(ax, ay, az, 0.0));
-        const double4 r = ld256(p.R + row);
-        v[0] += r.x * u.x; v[1] += r.y * u.y; v[2] += r.z * u.z;
-        v[3] += u.x * ax;  v[4] += u.y * ay;  v[5] += u.z * az;
-        v[6] += r.x * r.x; v[7] += r.y * r.y; v[8] += r.z * r.z;
-      }
+    }
+    if (row >= 0) {
+      v[0] = r0 * u0; v[1] = r1 * u1; v[2] = r2 * u2;
+      v[3] = u0 * w0; v[4] = u1 * w1; v[5] = u2 * w2;
+      v[6] = r0 * r0; v[7] = r1 * r1; v[8] = r2 * r2;
+    } else {
+#pragma unroll
+      for (int k = 0; k < kPcgNV; ++k) v[k] = 0.0;
     }
     pcg_grid_reduce(v, p.partials, grid, red, tot);
     pcg_coefficients(tot, it, p.max_iters, p.rtol2, sc_bb, sc_go, sc_ao, sc_a, sc_b, sc_rr, &sc_stop);
     if (sc_stop) break;
     const double a0 = sc_a[0], a1 = sc_a[1], a2 = sc_a[2], b0 = sc_b[0], b1 = sc_b[1], b2 = sc_b[2];
-    // ---- B: p = u + beta p; s = w + beta s; x += alpha p; r -= alpha s --------------------------------------------
-    for (int s = gwarp; s < p.nslices; s += nwarps) {
-      const int row = p.sell_row[s * kSellC + lane];
-      if (row >= 0) {
-        const double4 u = ld256(p.U + row), w = ld256(p.W + row);
-        double4 pp = ld256(p.P + row), ss = ld256(p.S + row);
-        pp.x = u.x + b0 * pp.x; pp.y = u.y + b1 * pp.y; pp.z = u.z + b2 * pp.z;
-        ss.x = w.x + b0 * ss.x; ss.y = w.y + b1 * ss.y; ss.z = w.z + b2 * ss.z;
-        st256(p.P + row, pp); st256(p.S + row, ss);
-        double4 x = ld256(p.X + row), r = ld256(p.R + row);
-        x.x += a0 * pp.x; x.y += a1 * pp.y; x.z += a2 * pp.z;
-        r.x -= a0 * ss.x; r.y -= a1 * ss.y; r.z -= a2 * ss.z;
-        st256(p.X + row, x); st256(p.R + row, r);
-      }
+    // ---- B: p = u + beta p; s = w + beta s; x += alpha p; r -= alpha s (registers); r published for the restriction ----
+    if (row >= 0) {
+      p0 = u0 + b0 * p0; p1 = u1 + b1 * p1; p2 = u2 + b2 * p2;
+      s0 = w0 + b0 * s0; s1 = w1 + b1 * s1; s2 = w2 + b2 * s2;
+      x0 += a0 * p0; x1 += a1 * p1; x2 += a2 * p2;
+      r0 -= a0 * s0; r1 -= a1 * s1; r2 -= a2 * s2;
+      st256(p.R + row, make_double4(r0, r1, r2, 0.0));
     }
     ++it;
     grid.sync();
@@ -299,9 +298,19 @@ k_pcg_coarse_w3(const PcgCoarseParams q) {
     coarse_restrict(q, gwarp, nwarps, lane);
     grid.sync();
     coarse_solve(q, ainv, yc, rc_s);
-    coarse_apply_rows(q, yc, gwarp, nwarps, lane);
+    if (row >= 0) {
+      u0 = d0 * r0; u1 = d1 * r1; u2 = d2 * r2;
+      if (in_p) {
+        const double4 y = yc[row / q.bsz];
+        if (d0 != 0.0) u0 += y.x;
+        if (d1 != 0.0) u1 += y.y;
+        if (d2 != 0.0) u2 += y.z;
+      }
+      st256(p.U + row, make_double4(u0, u1, u2, 0.0));
+    }
     grid.sync();
   }
+  if (row >= 0) st256(p.X + row, make_double4(x0, x1, x2, 0.0));
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     p.ctl->cg_iters = it;
     for (int c = 0; c < 3; ++c) { p.ctl->bnorm2[c] = sc_bb[c]; p.ctl->rnorm2[c] = sc_rr[c]; }

@@ -64,6 +64,8 @@ def run(frames=10000, loop_every=500, cpu_frames=150):
     line = {"metric": "rotAvg window calls/s on a growing graph (config 5)", "value": float(solved.sum() / lat[solved].sum() * 1e3),
             "unit": "calls/s", "frames": args.frames, "loop_every": args.loop_every, "wall_s_incl_parsing": wall,
             "local": stats(~glob), "global": stats(glob),
+            "global_calls": [{"views": int(c[2]), "edges": int(c[3]), "l1_iters": int(c[5]), "irls_iters": int(c[6]),
+                              "ms": float(c[7] * 1e3)} for c in calls[glob & solved]],
             "geodesic_rms_vs_ground_truth_rad": float(O.geodesic_rms(Q, Qgt, 1))}
     # the reference's own CPU path on the same stream: oracle/_ref/rotavg_reference = the source text of
     # ViewGraph::rotAvg + ral/l1_irls.cpp compiled by oracle/build_ref.py (dense stand-in solvers: window-sized problems

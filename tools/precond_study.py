@@ -12,6 +12,11 @@ stop when all converged - like the device kernels) for candidate preconditioners
   agg + coarse      the same plus an additive piecewise-constant coarse correction over unlimited stiff components
 
     python tools/precond_study.py --n 100000 --m 1000000 --snap 5,10,20,29
+    python tools/precond_study.py --coarse          # chain-like graphs: Jacobi vs Jacobi + coarse space (ira_coarse.cuh)
+
+Findings (n = 100 000, m = 1 000 000, L1): PCG iterations of the solve at IRLS iteration 10 / 20 / 29 - mutual pairs
+67 / 221 / 436, <= 3-node aggregates 45 / 89 / 132, <= 8 nodes 43 / 80 / 120, <= 32 nodes 43 / 80 / 121: exact blocks
+larger than 3 buy nothing (the stiff components are tiny, the rest of the spectrum is the spread of the robust weights).
 """
 import argparse
 import os
@@ -141,7 +146,36 @@ def coarse_additive(L, d, lab, base_apply, exact=False):
     return apply, nc
 
 
+def coarse_study():
+    """PCG iterations (rtol 1e-10) with Jacobi and with Jacobi + piecewise-constant coarse space over contiguous index
+    blocks (exact coarse solve), on the chain-like graphs: a config-5 stream graph, the reference's bundled fixture,
+    config 2.  The numbers quoted in irotavg_b200/csrc/ira_coarse.cuh."""
+    from oracle import rotavg_stream as RS
+
+    def test(name, n, f, I, w2, ncs=(32, 64, 128)):
+        L, d = laplacian(n, f, I, w2)
+        nf = n - f
+        B = np.random.default_rng(0).standard_normal((nf, 3))
+        dj = lambda R: R / d[:, None]
+        out = {"jacobi": pcg(L, B, dj, max_iters=20000)[1]}
+        for nc in ncs:
+            bsz = int(np.ceil(nf / nc))
+            M, ncc = coarse_additive(L, d, np.arange(nf) // bsz, dj, exact=True)
+            out[f"coarse{ncc}"] = pcg(L, B, M, max_iters=20000)[1]
+        print(name, "n", n, "m", len(I), out, flush=True)
+    ops, _ = RS.make_stream(n_frames=3000, loop_every=500, min_loop_gap=500)
+    I = np.array([(op[1], op[2]) for op in ops if op[0] == "E"])
+    test("stream, 3000 views, unit weights", 3000, 1, I, np.ones(len(I)))
+    test("stream, 3000 views, weights 1e-2..1e2", 3000, 1, I, 10 ** np.random.default_rng(1).uniform(-2, 2, len(I)))
+    b = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "bundled_graph.npz"))
+    test("bundled fixture, unit weights", 1832, 1, b["I"], np.ones(len(b["I"])))
+    g = G.kitti_like_graph()
+    test("config 2, unit weights", g.n, 1, g.I, np.ones(g.m))
+
+
 def main():
+    if "--coarse" in sys.argv:
+        return coarse_study()
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=100000)
     ap.add_argument("--m", type=int, default=1000000)
