@@ -8,7 +8,8 @@ ref_bundled_cli.npz   the reference CLI `l1_irls` on its own fixture ral/data/ra
                       (init_mst -> l1ra(5, 1e-3) -> irls(Geman-McClure, 5 deg, 50, 1e-3) -> quat_normalised,
                       ral/test.cpp:250-302), and the same with cost L1, Huber, L2; Q as [x y z w], weights.
 ref_small.npz         through the C entry points over irotavg::* on seeded synthetic graphs: all 14 costs (6 IRLS
-                      iterations, f = 3, edges in both orientations -> make_A's dropped-edge rule), make_A itself,
+                      iterations, f = 3, edges in both orientations -> make_A's dropped-edge rule), Talwar at 5 deg
+                      (rank-deficient: every edge of two free nodes gets weight 0), make_A itself,
                       log_map(delta_rel) per edge incl. the wrap / s < EPS rows, exp_map incl. the NaN -> 0 row,
                       init_mst (forward and backward tree edges), l1ra alone, l1ra -> irls on a banded view graph,
                       an identity-start (large-angle) window.
@@ -62,6 +63,10 @@ def small():
         sg = 4 * SIGMA if cost == 12 else SIGMA   # Talwar at 5 deg zeroes every edge of some node on this graph
         Q, w, it = R.irls(gq.QQ, gq.I, cost, sg, gq.Q0, gq.f, 6, -1.0)
         out[f"quirk_c{cost}_Q"] = Q; out[f"quirk_c{cost}_weights"] = w; out[f"quirk_c{cost}_iters"] = np.int32(it)
+    # Talwar at 5 deg zeroes every edge of two free nodes here: D A loses rank, SuiteSparseQR's rank detection declares
+    # their columns dead and returns x = 0 for them (the basic solution, ral/l1_irls.cpp:550)
+    Q, w, it = R.irls(gq.QQ, gq.I, 12, SIGMA, gq.Q0, gq.f, 6, -1.0)
+    out["quirk_talwar5_Q"] = Q; out["quirk_talwar5_weights"] = w
     out["quirk_A"] = R.make_A(gq.n, gq.f, gq.I)
     out["quirk_residual"] = R.residual(gq.I, gq.QQ, gq.Q0)
     out["ident_residual"] = R.residual(gi.I, gi.QQ, gi.Q0)

@@ -67,6 +67,20 @@ def test_oracle_irls_all_costs_vs_reference(ref_small, cost):
     assert wclose(r.weights, ref_small[f"quirk_c{cost}_weights"], 1e-7)
 
 
+def test_oracle_rank_deficient_talwar_vs_reference(ref_small):
+    """Talwar at 5 deg gives every edge of two free nodes weight 0: the reference's SPQR call returns its basic
+    solution (dead columns -> x = 0); the oracle's minimum-norm least squares agrees because the dead columns are
+    exactly zero."""
+    gq = graphs()[0]
+    r = O.irls(gq.QQ, gq.I, None, O.TALWAR, SIGMA, gq.Q0, gq.f, 6, -1.0, solver="lstsq")
+    w = ref_small["quirk_talwar5_weights"]
+    live = np.zeros(gq.n)
+    np.add.at(live, gq.I[:, 0], w > 0); np.add.at(live, gq.I[:, 1], w > 0)
+    assert (live[gq.f:] == 0).sum() >= 1                                         # the case is really rank-deficient
+    assert O.geodesic_rms(r.Q, ref_small["quirk_talwar5_Q"], gq.f) <= 1e-12
+    assert np.array_equal(r.weights, w)
+
+
 def test_oracle_kernels_vs_reference(ref_small):
     gq, gk, gw, gi = graphs()
     A = O.make_A(gq.n, gq.f, gq.I)
@@ -152,6 +166,16 @@ def test_gpu_irls_all_costs_vs_reference(solver, ref_small, cost):
     assert info.iters == int(ref_small[f"quirk_c{cost}_iters"])
     assert O.geodesic_rms(Q, ref_small[f"quirk_c{cost}_Q"], gq.f) <= 1e-8
     assert wclose(w, ref_small[f"quirk_c{cost}_weights"], 1e-5)
+
+
+@pytest.mark.gpu
+def test_gpu_rank_deficient_talwar_vs_reference(solver, ref_small):
+    """The same rank-deficient case on the device: rows whose edges all have weight 0 have a zero diagonal, PCG leaves
+    their x at 0 - SPQR's basic solution."""
+    gq = graphs()[0]
+    Q, w, info = solver.irls(gq.QQ, gq.I, None, O.TALWAR, SIGMA, gq.Q0, gq.f, 6, -1.0)
+    assert O.geodesic_rms(Q, ref_small["quirk_talwar5_Q"], gq.f) <= 1e-8
+    assert np.array_equal(w, ref_small["quirk_talwar5_weights"])
 
 
 @pytest.mark.gpu
