@@ -556,6 +556,7 @@ def run_ours(args):
         if os.path.exists(tp):
             with open(tp) as fh:
                 traffic = json.load(fh)
+        tr_pcg = (traffic or {}).get("k_pcg_smem" if pinfo.pcg_kernel == 4 else "k_pcg_persistent_reg") or {}
         spmv_phase_us = ph.get("spmv_us_per_phase")
         kname = {1: "k_pcg_persistent (vectors in HBM)", 2: "k_pcg_persistent_reg (state in registers)",
                  3: "k_pcg_persistent_reg_mw", 4: "k_pcg_smem (state in registers, matrix in shared memory)",
@@ -564,14 +565,15 @@ def run_ours(args):
             "kernel": kname + ": persistent PCG solve (SELL SpMV + Chronopoulos-Gear PCG, 3 RHS); one launch per IRLS iteration",
             "pcg_kernel_id": pinfo.pcg_kernel,
             "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "peak_source": peak_src, "traffic": (traffic or {}).get("k_pcg_smem" if pinfo.pcg_kernel == 4 else "k_pcg_persistent_reg"),
+            "peak_source": peak_src, "traffic": tr_pcg.get("dram_bytes_per_launch"), "traffic_source": tr_pcg.get("source"),
             "algorithmic_bytes_per_launch": K * per_iter_bytes, "algorithmic_bytes_per_pcg_iteration": per_iter_bytes,
             "pcg_iterations_per_launch": K, "launch_us": launch_us, "launches_timed": pcg["launches"],
             "share_of_step": prof_share.get("pcg"),
             "us_per_pcg_iteration": launch_us / max(K, 1e-9),
             "note": "launch_us = CUDA events on the launch stream around each of the 30 PCG-kernel launches of one step "
-                    "(profile mode, same call as the timed steps).  The kernel's data (matrix in shared memory, u in L2) never "
-                    "leaves the chip between PCG iterations, so the HBM roofline is a bound it cannot reach: the SpMV phase "
+                    "(profile mode, same call as the timed steps).  traffic (ncu, DRAM bytes per launch) is ~2 % of the "
+                    "algorithmic bytes: the matrix and vectors come from HBM once per launch and stay in registers / L2 for "
+                    "its ~48 PCG iterations, so the HBM roofline is a bound the kernel cannot reach: the SpMV phase "
                     "sits on the L2 sector bandwidth of the 2m random 32 B gathers (tools/microbench.cu: >= 10.4 us), the rest "
                     "is two grid barriers per iteration.",
             "spmv_phase": {"us_per_phase_incl_reduction": spmv_phase_us, "algorithmic_bytes": spmv_bytes,

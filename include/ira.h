@@ -59,7 +59,8 @@ typedef struct ira_options {
   double  pair_theta;      /* block-Jacobi pairing threshold: nodes v,u whose edge has strength
                               w2_vu / sqrt(d_v d_u) >= pair_theta and who are each other's strongest
                               neighbour are preconditioned together (2x2 blocks, as an additive
-                              coarse correction); 0 = plain Jacobi.  Default 0.2                  */
+                              coarse correction); 0 = plain Jacobi.  Default 0.5 (sweep: profiles/
+                              r02_sweep_theta_*.json)                                             */
   int32_t cg_check_every;  /* host polls the device-side convergence flag every this many iters   */
   int32_t lanes_per_row;   /* 0 = SELL-32 thread-per-row kernels (default); 2..32 = CSR kernels
                               with that many lanes per row (forces solver 1)                       */
@@ -95,7 +96,7 @@ typedef struct ira_options {
   int32_t reserved[2];
   double  pair_theta3;     /* a still-single node joins the pair holding its strongest neighbour when that edge's
                               normalised strength is >= pair_theta3 (3x3 blocks, inverted exactly); 0 = pairs only.
-                              Default 0.05                                                                      */
+                              Default 0.001                                                                     */
 } ira_options;
 
 #define IRA_STATS_MAX_ITERS 256

@@ -1071,8 +1071,8 @@ ira_status ira_options_default(ira_options* o) {
   o->device = -1;
   o->cg_max_iters = 20000;
   o->cg_rtol = 1e-10;
-  o->pair_theta = 0.2;
-  o->pair_theta3 = 0.05;
+  o->pair_theta = 0.5;       // measured optimum on configs[2], profiles/r02_sweep_theta_{1,2,3,broad}.json
+  o->pair_theta3 = 0.001;
   o->cg_check_every = 16;
   o->lanes_per_row = 0;
   o->world_size = 1;

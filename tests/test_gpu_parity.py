@@ -321,7 +321,7 @@ def test_three_by_three_blocks_vs_pairs_and_oracle(built_lib):
         with ira.Solver(solver=kind) as s3:
             Q3, w3, i3 = s3.irls(g.QQ, g.I, None, O.L1, SIGMA, g.Q0, g.f, 20, -1.0)
         assert i3.cg_hit_max == 0
-        assert sum(i3.cg_iters[10:]) * 1.3 < sum(i2.cg_iters[10:]), (kind, i2.cg_iters, i3.cg_iters)
+        assert sum(i3.cg_iters[10:]) * 1.2 < sum(i2.cg_iters[10:]), (kind, i2.cg_iters, i3.cg_iters)
         assert np.allclose(i3.scores, ref.scores, rtol=1e-6, atol=1e-12)
         assert O.geodesic_rms(Q3, ref.Q, g.f) <= RMS_TOL
         assert np.allclose(w3, ref.weights, rtol=1e-5, atol=1e-8)
