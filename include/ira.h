@@ -75,6 +75,10 @@ typedef struct ira_options {
                               +8 = one GPU only: the barrier-free kernel of the multi-GPU path
                               (self-validating data instead of grid barriers; measured slower, kept for A/B);
                               +128 = never use the two-level kernel for small / medium graphs (ira_coarse.cuh; A/B);
+                              +256 = two-level kernel: dense 64-block coarse space only, never the tridiagonal one of
+                              up to 1 024 blocks (A/B);
+                              (ira_options_default presets this field from the environment variable IRA_SOLVER, so that
+                              callers taking the defaults - the C++ adapters, the CLI - can be A/B-tested too)
                               +64 = deal the SELL slices to the blocks round-robin instead of balanced by entries (A/B);
                               +32 = the matrix-in-shared-memory kernel (ira_pcg2.cuh; measured SLOWER: it leaves the SM
                               28 KB of L1 and the gathers lose their memory-level parallelism; kept for A/B)   */
@@ -120,7 +124,8 @@ typedef struct ira_stats {
   double  t_pcg_ms, pcg_spmv_ms, pcg_update_ms, pcg_kernel_ms;
   /* which linear-solve driver ran (ABI 2): 0 one kernel per CG step, 1 k_pcg_persistent (vectors in HBM),
    * 2 k_pcg_persistent_reg, 3 k_pcg_persistent_reg_mw, 4 k_pcg_smem (matrix in shared memory), 5 peer-memory kernels,
-   * 6 single-block window solver, 7 k_pcg_coarse_w3 (two-level: Jacobi + coarse space, ira_coarse.cuh) */
+   * 6 single-block window solver, 7 k_pcg_coarse_w3 (two-level: Jacobi + dense coarse space, ira_coarse.cuh),
+   * 8 the same with the tridiagonal coarse operator (cyclic reduction, <= 1 024 blocks) */
   int32_t pcg_kernel;
   int32_t reserved_stats;
 } ira_stats;

@@ -40,9 +40,13 @@ struct DevBuf {
   size_t cap = 0;
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    // A buffer that has to GROW belongs to a growing graph (the rotAvg stream: every global call is a few hundred
+    // views larger than the last, and re-allocating ~40 buffers costs more than the solve): double it.  First
+    // allocations, and anything beyond 1 GB, get 12.5 % of headroom only.
+    size_t want = bytes + bytes / 8 + 256;
+    if (p && bytes < (size_t(1) << 30)) want = std::max(want, 2 * cap);
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
-    const size_t want = bytes + bytes / 8 + 256;
     cudaError_t e = cudaMalloc(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;
@@ -120,7 +124,9 @@ struct ira_context {
   // two-level PCG for small / medium graphs (ira_coarse.cuh)
   DevBuf coarse_AC, coarse_RC;
   bool coarse_ok = false;
-  int coarse_nc = 0, coarse_bsz = 0, coarse_smem = 0;
+  int coarse_nc = 0, coarse_bsz = 0, coarse_smem = 0, coarse_tri_n = 0;
+  int tri_bsz = 0;                   // > 0: chain-like graph, tridiagonal coarse operator with blocks of this many rows
+  bool sell_index_order = false;     // SELL pattern in row order (the TRI kernel's blocks are lane groups)
   int cur_cost = -1;         // cost of the running irls call (the L1 family keeps the block-Jacobi kernels)
   DevBuf slice_map;          // balanced slice -> (block, warp) map of k_pcg_persistent_reg (PcgRegParams::slice_map)
   bool slice_map_ok = false;
@@ -824,7 +830,7 @@ ira_status build_sell(ira_context* h) {
   IRA_CUDA(h, h->slice_off.reserve(sizeof(int) * ((size_t)h->nslices + 1)));
   IRA_CUDA(h, cudaMemsetAsync(h->slice_cnt.p, 0, sizeof(int) * ((size_t)h->nslices + 1), h->stream));
   k_sell_sort<<<nwin, kSellSigma, 0, h->stream>>>(h->rowptr.as<int>(), n, h->sell_row.as<int>(),
-                                                 h->slice_width.as<int>(), h->slice_cnt.as<int>());
+                                                 h->slice_width.as<int>(), h->slice_cnt.as<int>(), h->sell_index_order ? 1 : 0);
   IRA_TRY(launch_check(h, "k_sell_sort"));
   size_t tmp_bytes = 0;
   IRA_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->slice_cnt.as<int>(), h->slice_off.as<int>(),
@@ -893,10 +899,50 @@ ira_status plan_slice_map(ira_context* h) {
 
 // Two-level PCG (ira_coarse.cuh) for graphs of up to kCoarseMaxRows nodes: partition of the node indices into
 // nc <= 64 contiguous blocks; shared memory for the three nc x nc inverses.
+// Host-only decision, before the SELL pattern is built: is this a chain-like graph for the tridiagonal coarse
+// operator (ira_coarse.cuh, TRI)?  Blocks of 8, 16 or 32 consecutive rows (lane groups of a warp once the SELL pattern
+// is in index order), at most kTriMax of them, and at most 2 % of the edges may reach beyond the adjacent block (those
+// are lumped onto the diagonal of the coarse operator).  +256: dense 64-block variant only (A/B).
+void plan_coarse_tri(ira_context* h, const int32_t* I_pairs) {
+  h->tri_bsz = 0;
+  const int n = h->n, nfree = h->n - h->f;
+  if ((h->opt.solver & (128 | 256)) || h->opt.lanes_per_row >= 2 || h->pcg_blocks_per_sm <= 0 || n > kCoarseMaxRows ||
+      nfree <= kTriMinBlock * kCoarseMax)
+    return;
+  for (int bsz = kTriMinBlock; bsz <= kSellC; bsz *= 2) {
+    if (cdiv(n, bsz) > kTriMax) continue;
+    if (cdiv(n, bsz) <= kCoarseMax) break;
+    int64_t far = 0;
+    for (int64_t k = 0; k < h->m; ++k) {
+      const int d = I_pairs[2 * k] / bsz - I_pairs[2 * k + 1] / bsz;
+      if (d > 1 || d < -1) ++far;
+    }
+    if (far * 50 <= h->m) { h->tri_bsz = bsz; return; }
+  }
+}
+
 ira_status plan_coarse(ira_context* h, const int32_t* I_pairs) {
   h->coarse_ok = false;
   const int n = h->n, nfree = h->n - h->f;
   if (h->pcg_blocks_per_sm <= 0 || h->nslices <= 0 || n > kCoarseMaxRows || nfree < 128) return IRA_OK;
+  // Tridiagonal coarse operator (ira_coarse.cuh, TRI): decided before the SELL build (plan_coarse_tri), resources here.
+  h->coarse_tri_n = 0;
+  if (h->tri_bsz > 0 && h->sell_index_order) {
+    const int bsz = h->tri_bsz, nc = cdiv(n, bsz);
+    int N = 1;
+    while (N < nc) N <<= 1;
+    const int bytes = (int)sizeof(double) * 18 * N;
+    int nb = 0;
+    if (N <= kTriMax && cudaFuncSetAttribute(k_pcg_coarse_w3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_coarse_w3<true>, kCoarseThreads, (size_t)bytes) == cudaSuccess && nb >= 1) {
+      IRA_CUDA(h, h->coarse_AC.reserve(sizeof(double) * 6 * (size_t)N));
+      IRA_CUDA(h, h->coarse_RC.reserve(sizeof(double4) * (size_t)nc));
+      h->coarse_nc = nc; h->coarse_bsz = bsz; h->coarse_smem = bytes; h->coarse_tri_n = N;
+      h->coarse_ok = true;
+      return IRA_OK;
+    }
+    cudaGetLastError();
+  }
   const int bsz = std::max(2, cdiv(n, kCoarseMax));
   const int nc = cdiv(n, bsz);
   if (nc < 2 || nc > kCoarseMax) return IRA_OK;
@@ -911,9 +957,9 @@ ira_status plan_coarse(ira_context* h, const int32_t* I_pairs) {
   }
   if (far * 50 > h->m) return IRA_OK;
   const int bytes = (int)sizeof(double) * (((3 * nc * nc + 3) & ~3) + 8 * nc);
-  if (cudaFuncSetAttribute(k_pcg_coarse_w3, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) { cudaGetLastError(); return IRA_OK; }
+  if (cudaFuncSetAttribute(k_pcg_coarse_w3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) { cudaGetLastError(); return IRA_OK; }
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_coarse_w3, kCoarseThreads, (size_t)bytes) != cudaSuccess || nb < 1) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pcg_coarse_w3<false>, kCoarseThreads, (size_t)bytes) != cudaSuccess || nb < 1) {
     cudaGetLastError();
     return IRA_OK;
   }
@@ -939,14 +985,15 @@ ira_status launch_pcg_coarse(ira_context* h, const double4* rhs, double4* xout) 
   q.sell_pos = h->sell_pos.as<int>();
   q.f = h->f; q.nc = h->coarse_nc; q.bsz = h->coarse_bsz;
   q.AC = h->coarse_AC.as<double>(); q.RC = h->coarse_RC.as<double4>();
+  q.tri_n = h->coarse_tri_n;
   // one slice per warp, 12 warps per block: as few blocks as hold the slices (cheap grid barriers)
   const int grid = std::max(1, cdiv(h->nslices, kCoarseThreads / 32));
   if (grid > h->sms) { h->err = "two-level PCG: more slices than resident warps"; return IRA_ERR_INVALID_ARG; }
   void* args[] = {(void*)&q};
-  IRA_CUDA(h, cudaLaunchCooperativeKernel((void*)k_pcg_coarse_w3, dim3(grid), dim3(kCoarseThreads), args,
-                                          (size_t)h->coarse_smem, h->stream));
+  IRA_CUDA(h, cudaLaunchCooperativeKernel(h->coarse_tri_n ? (void*)k_pcg_coarse_w3<true> : (void*)k_pcg_coarse_w3<false>, dim3(grid),
+                                          dim3(kCoarseThreads), args, (size_t)h->coarse_smem, h->stream));
   h->launches++;
-  h->pcg_kernel = 7;
+  h->pcg_kernel = h->coarse_tri_n ? 8 : 7;
   return IRA_OK;
 }
 
@@ -1079,6 +1126,8 @@ ira_status ira_options_default(ira_options* o) {
   o->rank = 0;
   o->profile = 0;
   o->peer_min_rows = 120000;
+  // A/B aid for callers that take the defaults (the C++ adapters, the CLI): IRA_SOLVER=<bits> presets `solver`
+  if (const char* e = getenv("IRA_SOLVER")) o->solver = atoi(e);
   return IRA_OK;
 }
 
@@ -1165,10 +1214,23 @@ ira_status ira_problem_upload(ira_handle h, int64_t m, int64_t n_total, int32_t 
   // SELL padding blow-up (heavy-tailed degrees) falls back to the CSR sub-warp kernels
   h->fmt_csr = h->opt.lanes_per_row >= 2;
   h->sell_built = false;
+  h->sell_index_order = false;
+  h->tri_bsz = 0;
   if (!h->fmt_csr) {
+    const bool alone = h->opt.world_size <= 1 ||
+                       ((h->opt.shard_mode == 1 || h->opt.shard_mode == 2) && n_total < (int64_t)h->opt.peer_min_rows);
+    if (alone) plan_coarse_tri(h, I_pairs);
+    h->sell_index_order = h->tri_bsz > 0;
     IRA_TRY(build_sell(h));
     h->sell_built = true;
-    if (h->sell_total > 3ll * std::max(h->nnz, 1) + 64ll * kSellSigma) h->fmt_csr = true;
+    if (h->sell_total > 3ll * std::max(h->nnz, 1) + 64ll * kSellSigma) {
+      if (h->sell_index_order) {                     // index order pads too much after all: degree-sorted windows
+        h->sell_index_order = false;
+        h->tri_bsz = 0;
+        IRA_TRY(build_sell(h));
+      }
+      if (h->sell_total > 3ll * std::max(h->nnz, 1) + 64ll * kSellSigma) h->fmt_csr = true;
+    }
   }
   // whole graph on every rank and too small to be worth partitioning: replicated single-GPU solves
   h->replicated = h->opt.world_size > 1 && (h->opt.shard_mode == 1 || h->opt.shard_mode == 2) &&
@@ -1652,6 +1714,9 @@ ira_status l1decode_pd_device(ira_context* h, int pdmaxiter, int* newton_cg_iter
     IRA_TRY(fetch_pdctl(h));
     IRA_TRY(fetch_ctl(h));
     *newton_cg_iters += h->h_ctl->cg_iters;
+    if (getenv("IRA_DEBUG") && atoi(getenv("IRA_DEBUG")) >= 2)
+      fprintf(stderr, "[ira]   newton solve: %d PCG its, |r|^2 %.17g %.17g %.17g, |b|^2 %.17g %.17g %.17g\n", h->h_ctl->cg_iters,
+              h->h_ctl->rnorm2[0], h->h_ctl->rnorm2[1], h->h_ctl->rnorm2[2], h->h_ctl->bnorm2[0], h->h_ctl->bnorm2[1], h->h_ctl->bnorm2[2]);
     for (int k = 0; k < 3; ++k)
       if (!(h->h_ctl->rnorm2[k] <= h->opt.cg_rtol * h->opt.cg_rtol * h->h_ctl->bnorm2[k])) { *hit_max += 1; break; }
     const PdCtl& c = *h->h_pdctl;
@@ -1908,8 +1973,19 @@ extern "C" ira_status ira_l1ra_irls(ira_handle h, int64_t m, int64_t n_total, in
   ira_status rc = ira_l1ra_resident(h, l1_max_iters, l1_change_th, l1_iters_out, nullptr, &l1_stats);
   if (rc != IRA_OK && rc != IRA_ERR_NONFINITE) return rc;
   h->start_mode = 1;                                       // irls continues from l1ra's rotations
-  rc = ira_irls_resident(h, cost, sigma, irls_max_iters, irls_change_th, irls_iters_out, nullptr, irls_stats);
+  static thread_local ira_stats own_stats;
+  ira_stats* const ist = irls_stats ? irls_stats : &own_stats;
+  rc = ira_irls_resident(h, cost, sigma, irls_max_iters, irls_change_th, irls_iters_out, nullptr, ist);
   h->start_mode = 0;
+  if (getenv("IRA_DEBUG")) {
+    fprintf(stderr, "[ira] l1ra_irls n %lld m %lld f %d: l1ra %d its, %d Newton PCG its, hit %d, score %.17g; irls %d its, %d PCG its, hit %d, "
+            "kernel %d, score %.17g; %.3f ms\n",
+            (long long)n_total, (long long)m, f, l1_stats.irls_iters, l1_stats.cg_iters_total, l1_stats.cg_hit_max,
+            l1_stats.irls_iters > 0 ? l1_stats.score[std::min(l1_stats.irls_iters, IRA_STATS_MAX_ITERS) - 1] : 0.0, ist->irls_iters,
+            ist->cg_iters_total, ist->cg_hit_max, ist->pcg_kernel,
+            ist->irls_iters > 0 ? ist->score[std::min(ist->irls_iters, IRA_STATS_MAX_ITERS) - 1] : 0.0,
+            1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  }
   if (irls_stats) irls_stats->cg_hit_max += l1_stats.cg_hit_max;   // unconverged Newton solves of the l1ra stage count too
   if (rc != IRA_OK && rc != IRA_ERR_NONFINITE) return rc;
   IRA_TRY(ira_problem_download(h, Q, ld_q, weights));

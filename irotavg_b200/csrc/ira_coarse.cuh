@@ -26,6 +26,18 @@
 //     D  y_c = A_c^-1 r_c from shared memory (every block, redundantly), u = D^-1 r + y_c[block(row)]   -> barrier 4
 // Four barriers instead of two per iteration (2-3x the cost of a one-level iteration on these small grids) for 6-13x
 // fewer iterations.
+//
+// Tridiagonal variant (TRI, graphs of more than ~500 free nodes).  With 64 blocks the iteration count still grows like
+// the block length (numpy, 9 500-view stream graph, unit weights: 366 iterations with 64 blocks, 108 with 250, 41 with
+// 950).  For CONTIGUOUS index blocks P^T L P is tridiagonal up to the loop closures, and keeping only its tridiagonal
+// part T (the far couplings stay on the diagonal: T is diagonally dominant, SPD) costs little: 138 / 96 / 78 / 65
+// iterations with 250 / 500 / 950 / 1 900 blocks, the same again with the dense 64-block space added on top.  So
+// nc grows to <= 1 024 blocks of >= 8 rows, and every thread block solves T y = r_c by cyclic reduction in its shared
+// memory: the multipliers of the log2(nc) elimination levels are computed once per solve (5 doubles per coarse unknown
+// and coordinate), an application is 2 log2(nc) + 1 short block-synchronous steps.  A dead pivot (floating component,
+// empty block) switches that unknown off exactly as in the dense variant (T restricted to the others).  The SELL
+// pattern of such a graph is built in index order, a block of the partition is a group of lanes of one warp, and the
+// restriction happens in registers: three grid barriers per iteration instead of four.
 #pragma once
 #include "ira_l1ra.cuh"
 
@@ -34,14 +46,17 @@ namespace ira {
 constexpr int kCoarseMax = 64;          // coarse unknowns per coordinate (3 x 64 x 64 doubles = 96 KB of shared memory)
 constexpr int kCoarseThreads = 384;     // >= kPcgNV warps: pcg_grid_reduce gives each of its 9 sums to one warp
 constexpr int kCoarseMaxRows = 32768;   // larger graphs keep the one-level kernels (148 x 12 warps hold 56 832 rows)
+constexpr int kTriMax = 1024;           // tridiagonal variant: coarse unknowns per coordinate (6 x 3 x 1024 doubles = 144 KB)
+constexpr int kTriMinBlock = 8;         // rows per block of the partition at least (the window edges must stay within adjacent blocks)
 
 struct PcgCoarseParams {
   PcgW3Params w;                        // matrix (3 weights per entry), vectors, partials, ctl
   const int* sell_pos;                  // row -> SELL position
   int f;                                // rows < f are fixed (never unknowns, never in P)
   int nc, bsz;                          // coarse size and rows per block of the partition: block(v) = v / bsz
-  double* AC;                           // [3][nc][nc] assembled coarse matrices (global scratch)
+  double* AC;                           // [3][nc][nc] assembled coarse matrices (global scratch); TRI: [2][3][tri_n] diagonal, coupling to block a - 1
   double4* RC;                          // [nc] coarse residual of the current iteration
+  int tri_n;                            // TRI: nc padded to a power of two (0: dense variant)
 };
 
 // r_c = P^T r: warp a sums the rows of block a in a fixed order (lane-strided partial sums, butterfly).
@@ -83,14 +98,136 @@ __device__ __forceinline__ void coarse_solve(const PcgCoarseParams& q, const dou
   __syncthreads();
 }
 
+
+// ---- tridiagonal coarse operator -------------------------------------------------------------------------------------
+// TRI runs on a SELL pattern built in INDEX order (ira_api.cu: build_sell with sell_index_order; view graphs have
+// near-uniform degrees, so nothing is lost to padding): slice k holds rows 32k .. 32k + 31, a block of the partition
+// (bsz = 8, 16 or 32 rows) is an aligned group of lanes of ONE warp, and r_c = P^T r comes straight from the registers:
+// a fixed-order butterfly over the group, no barrier and no round trip of r through global memory.
+__device__ __forceinline__ void coarse_restrict_tri(const PcgCoarseParams& q, int gwarp, int lane, double cx, double cy, double cz) {
+  for (int o = q.bsz >> 1; o > 0; o >>= 1) {
+    cx += __shfl_xor_sync(0xffffffffu, cx, o);
+    cy += __shfl_xor_sync(0xffffffffu, cy, o);
+    cz += __shfl_xor_sync(0xffffffffu, cz, o);
+  }
+  const int a = (gwarp * kSellC + lane) / q.bsz;
+  if ((lane & (q.bsz - 1)) == 0 && a < q.nc) st256(q.RC + a, make_double4(cx, cy, cz, 0.0));
+}
+
+// Shared-memory layout of the TRI variant: six [3][N] arrays.
+struct TriSmem {
+  double *BI, *L1, *L2, *M1, *M2, *Y;      // 1 / pivot, coupling to j - s, coupling to j + s, forward multipliers, work vector
+};
+__device__ __forceinline__ TriSmem tri_smem(unsigned char* base, int N) {
+  double* d = reinterpret_cast<double*>(base);
+  TriSmem t;
+  t.BI = d; t.L1 = d + 3 * N; t.L2 = d + 6 * N; t.M1 = d + 9 * N; t.M2 = d + 12 * N; t.Y = d + 15 * N;
+  return t;
+}
+
+// Cyclic-reduction factorisation of the three tridiagonal matrices (diag TD, coupling to the previous unknown TL), in
+// every block's shared memory, identical arithmetic everywhere.  Level l (stride s = 2^l): the active unknowns are
+// i with (i + 1) % s == 0; those with (i + 1) % 2s == s are eliminated into their neighbours i +- s, which stay.
+__device__ __forceinline__ void tri_factor(const PcgCoarseParams& q, const TriSmem& t) {
+  const int N = q.tri_n;
+  double* const D0 = t.Y;                                      // original diagonal: the scale of the dead-pivot test
+  for (int k = threadIdx.x; k < 3 * N; k += blockDim.x) {
+    const int c = k / N, a = k % N;
+    const double d = a < q.nc ? __ldcg(q.AC + (size_t)c * N + a) : 1.0;
+    t.BI[k] = d; D0[k] = d;
+    t.L1[k] = a < q.nc ? __ldcg(q.AC + (size_t)(3 + c) * N + a) : 0.0;
+    t.L2[k] = 0.0; t.M1[k] = 0.0; t.M2[k] = 0.0;
+  }
+  __syncthreads();
+  for (int s = 1; s < N; s <<= 1) {
+    const int cnt = N / (2 * s), off = N - N / s;
+    for (int k = threadIdx.x; k < 3 * cnt; k += blockDim.x) {
+      const int c = k / cnt, kk = k % cnt;
+      const int i = 2 * s * (kk + 1) - 1, jl = i - s, jr = i + s;
+      double* const B = t.BI + c * N; double* const lo = t.L1 + c * N;
+      const double bl = B[jl], sl = D0[c * N + jl];
+      const double il = (sl > 0.0 && bl > 1e-12 * sl) ? 1.0 / bl : 0.0;
+      const double ci = lo[i];                                 // coupling i <-> jl
+      const double k1 = ci * il;
+      double k2 = 0.0, cr = 0.0;
+      if (jr < N) {
+        const double br = B[jr], sr = D0[c * N + jr];
+        cr = lo[jr];                                           // coupling jr <-> i
+        k2 = cr * ((sr > 0.0 && br > 1e-12 * sr) ? 1.0 / br : 0.0);
+      }
+      const double lo_jl = lo[jl];
+      t.M1[c * N + off + kk] = k1; t.M2[c * N + off + kk] = k2;
+      t.L2[c * N + jl] = ci;                                   // jl is solved at this level: its coupling to jl + s = i
+      B[i] -= ci * k1 + cr * k2;
+      lo[i] = -lo_jl * k1;                                     // coupling i <-> i - 2s
+    }
+    __syncthreads();
+    // the eliminated unknowns keep 1 / pivot from here on (their pivots were read by both neighbours above; the next
+    // level touches only unknowns that stay, so no barrier is needed after this pass)
+    for (int k = threadIdx.x; k < 3 * cnt; k += blockDim.x) {
+      const int c = k / cnt, j = s - 1 + 2 * s * (k % cnt);
+      const double b = t.BI[c * N + j], sc = D0[c * N + j];
+      t.BI[c * N + j] = (sc > 0.0 && b > 1e-12 * sc) ? 1.0 / b : 0.0;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int c = threadIdx.x;
+    const double b = t.BI[c * N + N - 1], sc = D0[c * N + N - 1];
+    t.BI[c * N + N - 1] = (sc > 0.0 && b > 1e-12 * sc) ? 1.0 / b : 0.0;
+  }
+  __syncthreads();
+}
+
+// y_c = T^-1 r_c for the three coordinates: forward elimination with the stored multipliers, back substitution.
+// N is a power of two: every index split is a shift.
+__device__ __forceinline__ void tri_solve(const PcgCoarseParams& q, const TriSmem& t) {
+  const int N = q.tri_n;
+  const int lgN = 31 - __clz(N);
+  for (int a = threadIdx.x; a < N; a += blockDim.x) {
+    double4 r = make_double4(0, 0, 0, 0);
+    if (a < q.nc) r = ld256(q.RC + a);
+    t.Y[a] = r.x; t.Y[N + a] = r.y; t.Y[2 * N + a] = r.z;
+  }
+  __syncthreads();
+  for (int l = 0; l < lgN; ++l) {
+    const int s = 1 << l, lgc = lgN - l - 1, cnt = 1 << lgc, off = N - (N >> l);
+    for (int k = threadIdx.x; k < 3 * cnt; k += blockDim.x) {
+      const int c = k >> lgc, kk = k & (cnt - 1);
+      const int i = ((kk + 1) << (l + 1)) - 1;
+      double* const Y = t.Y + c * N;
+      double y = Y[i] - t.M1[c * N + off + kk] * Y[i - s];
+      if (i + s < N) y -= t.M2[c * N + off + kk] * Y[i + s];
+      Y[i] = y;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) t.Y[threadIdx.x * N + N - 1] *= t.BI[threadIdx.x * N + N - 1];
+  __syncthreads();
+  for (int l = lgN - 1; l >= 0; --l) {
+    const int s = 1 << l, lgc = lgN - l - 1, cnt = 1 << lgc;
+    for (int k = threadIdx.x; k < 3 * cnt; k += blockDim.x) {
+      const int c = k >> lgc, kk = k & (cnt - 1);
+      const int j = s - 1 + (kk << (l + 1));
+      double* const Y = t.Y + c * N;
+      double y = Y[j] - t.L2[c * N + j] * Y[j + s];
+      if (j >= s) y -= t.L1[c * N + j] * Y[j - s];
+      Y[j] = y * t.BI[c * N + j];
+    }
+    __syncthreads();
+  }
+}
+
+template <bool TRI>
 __global__ void __launch_bounds__(kCoarseThreads, 1)
 k_pcg_coarse_w3(const PcgCoarseParams q) {
   const PcgW3Params& p = q.w;
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(32) unsigned char dyn_smem[];
-  double* const ainv = reinterpret_cast<double*>(dyn_smem);                       // [3][nc][nc]
+  double* const ainv = reinterpret_cast<double*>(dyn_smem);                       // [3][nc][nc]          (dense variant)
   double4* const yc = reinterpret_cast<double4*>(ainv + ((3 * q.nc * q.nc + 3) & ~3));   // [nc], 32-byte aligned
   double4* const rc_s = yc + q.nc;                                                // [nc]
+  const TriSmem tri = tri_smem(dyn_smem, q.tri_n);                                // six [3][tri_n] arrays (TRI variant)
   __shared__ double red[kPcgNV * 32];
   __shared__ double tot[kPcgNV];
   __shared__ double sc_bb[3], sc_go[3], sc_ao[3], sc_a[3], sc_b[3], sc_rr[3];
@@ -123,6 +260,42 @@ k_pcg_coarse_w3(const PcgCoarseParams q) {
     st256(p.R + row, b);
     v[0] = r0 * r0; v[1] = r1 * r1; v[2] = r2 * r2;
   }
+  if (TRI) {
+    // diagonal (everything that leaves block a, fixed nodes and far blocks included) and the coupling to block a - 1;
+    // every lane walks its own row (index-ordered SELL), butterfly over the block's lanes: a fixed order.  T[a][a - 1] = T[a - 1][a] = the value row a computes.
+    const int N = q.tri_n;
+    if (gwarp < p.nslices) {
+      double dg0 = 0, dg1 = 0, dg2 = 0, lo0 = 0, lo1 = 0, lo2 = 0;
+      const int a = (gwarp * kSellC + lane) / q.bsz;
+      if (in_p) {
+        for (int j = 0; j < width; j += 4) {                          // widths are multiples of 4
+          int col[4]; double4 w3[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            col[t] = __ldg(p.sell_col + base + (int64_t)(j + t) * kSellC);
+            w3[t] = ldg256(p.sell_w3 + base + (int64_t)(j + t) * kSellC);
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (col[t] == row) continue;                             // padding slot
+            const int bc = col[t] >= q.f ? col[t] / q.bsz : -1;      // a fixed node grounds the block
+            if (bc != a) {
+              dg0 += w3[t].x; dg1 += w3[t].y; dg2 += w3[t].z;
+              if (bc >= 0 && bc == a - 1) { lo0 -= w3[t].x; lo1 -= w3[t].y; lo2 -= w3[t].z; }
+            }
+          }
+        }
+      }
+      for (int o = q.bsz >> 1; o > 0; o >>= 1) {
+        dg0 += __shfl_xor_sync(0xffffffffu, dg0, o); dg1 += __shfl_xor_sync(0xffffffffu, dg1, o); dg2 += __shfl_xor_sync(0xffffffffu, dg2, o);
+        lo0 += __shfl_xor_sync(0xffffffffu, lo0, o); lo1 += __shfl_xor_sync(0xffffffffu, lo1, o); lo2 += __shfl_xor_sync(0xffffffffu, lo2, o);
+      }
+      if ((lane & (q.bsz - 1)) == 0 && a < nc) {
+        q.AC[a] = dg0; q.AC[N + a] = dg1; q.AC[2 * N + a] = dg2;
+        q.AC[3 * N + a] = lo0; q.AC[4 * N + a] = lo1; q.AC[5 * N + a] = lo2;
+      }
+    }
+  } else
   for (int a = gwarp; a < nc; a += nwarps) {
     // lane l owns the coarse columns l and l + 32; every entry of every row of block a is visited in a fixed order
     double acc[3][2] = {{0, 0}, {0, 0}, {0, 0}};
@@ -166,10 +339,13 @@ k_pcg_coarse_w3(const PcgCoarseParams q) {
   // ---- set-up 2: every block inverts the three coarse matrices in its own shared memory (in-place Gauss-Jordan; SPD,
   //      no pivoting).  An empty block of the partition (all its nodes fixed) or a floating component leaves a zero
   //      pivot: that coarse unknown is switched off (row and column zeroed), the preconditioner stays SPD. --------------
-  for (int t = threadIdx.x; t < 3 * nc * nc; t += blockDim.x) ainv[t] = __ldcg(q.AC + t);
   __shared__ double piv_inv[3];
   __shared__ double scale[3 * kCoarseMax];
   __shared__ int dead[3 * kCoarseMax];
+  if (TRI) {
+    tri_factor(q, tri);
+  } else {
+  for (int t = threadIdx.x; t < 3 * nc * nc; t += blockDim.x) ainv[t] = __ldcg(q.AC + t);
   __syncthreads();
   for (int t = threadIdx.x; t < 3 * nc; t += blockDim.x) {          // row scales of the assembled matrices
     double m = 0.0;
@@ -222,14 +398,21 @@ k_pcg_coarse_w3(const PcgCoarseParams q) {
     }
   }
   __syncthreads();
+  }
   // ---- u0 = M^-1 b ---------------------------------------------------------------------------------------------
-  coarse_restrict(q, gwarp, nwarps, lane);
+  if (TRI) {
+    if (gwarp < p.nslices)
+      coarse_restrict_tri(q, gwarp, lane, in_p && d0 != 0.0 ? r0 : 0.0, in_p && d1 != 0.0 ? r1 : 0.0, in_p && d2 != 0.0 ? r2 : 0.0);
+  } else {
+    coarse_restrict(q, gwarp, nwarps, lane);
+  }
   grid.sync();
-  coarse_solve(q, ainv, yc, rc_s);
+  if (TRI) tri_solve(q, tri); else coarse_solve(q, ainv, yc, rc_s);
   if (row >= 0) {
     u0 = d0 * r0; u1 = d1 * r1; u2 = d2 * r2;
     if (in_p) {
-      const double4 y = yc[row / q.bsz];
+      const int blk = row / q.bsz;
+      const double4 y = TRI ? make_double4(tri.Y[blk], tri.Y[q.tri_n + blk], tri.Y[2 * q.tri_n + blk], 0.0) : yc[blk];
       if (d0 != 0.0) u0 += y.x;
       if (d1 != 0.0) u1 += y.y;
       if (d2 != 0.0) u2 += y.z;
@@ -290,18 +473,24 @@ k_pcg_coarse_w3(const PcgCoarseParams q) {
       s0 = w0 + b0 * s0; s1 = w1 + b1 * s1; s2 = w2 + b2 * s2;
       x0 += a0 * p0; x1 += a1 * p1; x2 += a2 * p2;
       r0 -= a0 * s0; r1 -= a1 * s1; r2 -= a2 * s2;
-      st256(p.R + row, make_double4(r0, r1, r2, 0.0));
+      if (!TRI) st256(p.R + row, make_double4(r0, r1, r2, 0.0));
     }
     ++it;
+    // ---- C: coarse residual (TRI: from the registers, no barrier before it); D: coarse solve and u = M^-1 r ------------
+    if (TRI) {
+      if (gwarp < p.nslices)
+        coarse_restrict_tri(q, gwarp, lane, in_p && d0 != 0.0 ? r0 : 0.0, in_p && d1 != 0.0 ? r1 : 0.0, in_p && d2 != 0.0 ? r2 : 0.0);
+    } else {
+      grid.sync();
+      coarse_restrict(q, gwarp, nwarps, lane);
+    }
     grid.sync();
-    // ---- C: coarse residual; D: coarse solve and u = M^-1 r ---------------------------------------------------------
-    coarse_restrict(q, gwarp, nwarps, lane);
-    grid.sync();
-    coarse_solve(q, ainv, yc, rc_s);
+    if (TRI) tri_solve(q, tri); else coarse_solve(q, ainv, yc, rc_s);
     if (row >= 0) {
       u0 = d0 * r0; u1 = d1 * r1; u2 = d2 * r2;
       if (in_p) {
-        const double4 y = yc[row / q.bsz];
+        const int blk = row / q.bsz;
+        const double4 y = TRI ? make_double4(tri.Y[blk], tri.Y[q.tri_n + blk], tri.Y[2 * q.tri_n + blk], 0.0) : yc[blk];
         if (d0 != 0.0) u0 += y.x;
         if (d1 != 0.0) u1 += y.y;
         if (d2 != 0.0) u2 += y.z;

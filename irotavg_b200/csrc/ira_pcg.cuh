@@ -33,11 +33,25 @@ constexpr int kPcgThreads = 768;   // 24 warps, <= 85 registers per thread
 // position (-1 beyond n) and the width (max degree) of every slice.
 __global__ void __launch_bounds__(kSellSigma)
 k_sell_sort(const int* __restrict__ rowptr, int n, int* __restrict__ sell_row, int* __restrict__ slice_width,
-            int* __restrict__ slice_cnt) {
+            int* __restrict__ slice_cnt, int index_order) {
   __shared__ unsigned long long key[kSellSigma];
   const int t = threadIdx.x;
   const int row = blockIdx.x * kSellSigma + t;
   const unsigned int deg = row < n ? (unsigned int)(rowptr[row + 1] - rowptr[row]) : 0u;
+  if (index_order) {
+    // chain-like view graphs on the two-level TRI path (ira_coarse.cuh): position = row, a slice is as wide as its
+    // widest row (degrees are near-uniform there)
+    sell_row[row] = row < n ? row : -1;
+    unsigned int w = deg;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if ((t & (kSellC - 1)) == 0) {
+      const int wd = ((int)w + 3) & ~3;
+      slice_width[row / kSellC] = wd;
+      slice_cnt[row / kSellC] = wd * kSellC;
+    }
+    return;
+  }
   // descending sort of this key = degree descending, then original order ascending; rows >= n last
   key[t] = row < n ? (((unsigned long long)deg + 1ull) << 32) | (unsigned long long)(kSellSigma - 1 - t) : 0ull;
   __syncthreads();

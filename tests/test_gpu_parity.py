@@ -339,8 +339,9 @@ def test_lanes_per_row_variants(built_lib, lpr):
 
 def test_two_level_pcg_on_chain_graphs(built_lib):
     """View graphs are chains (cond ~ n^2): the two-level kernel (Jacobi + piecewise-constant coarse space over index
-    blocks, ira_coarse.cuh) must give the same answer as the one-level kernels (solver +128) and the oracle, in several
-    times fewer PCG iterations; L1 keeps the block-Jacobi kernels."""
+    blocks, ira_coarse.cuh; tridiagonal coarse operator of up to 1 024 blocks by default, dense 64-block one with
+    solver +256) must give the same answer as the one-level kernels (solver +128) and the oracle, in several times
+    fewer PCG iterations; L1 keeps the block-Jacobi kernels."""
     import irotavg_b200 as ira
     from oracle import rotavg_stream as RS
     ops, Qgt = RS.make_stream(n_frames=2500, loop_every=900, min_loop_gap=600, sigma_n=0.01)
@@ -350,7 +351,7 @@ def test_two_level_pcg_on_chain_graphs(built_lib):
     Q0 = O.quat_mult(Qgt, G._exp_quat(rng.normal(0, 0.05, (Qgt.shape[0], 3))))
     Q0[0] = Qgt[0]
     res = {}
-    for sv in (0, 128):
+    for sv in (0, 256, 128):
         with ira.Solver(solver=sv) as s:
             Q, w, info = s.irls(QQ, I, None, O.GEMAN_MCCLURE, SIGMA, Q0, 1, 6, -1.0)
             Ql, il = s.l1ra(QQ, I, None, Q0, 1, 2, 1e-9)
@@ -358,15 +359,42 @@ def test_two_level_pcg_on_chain_graphs(built_lib):
         res[sv] = (Q, w, info, Ql, il, Q1, i1)
     ref = O.irls(QQ, I, None, O.GEMAN_MCCLURE, SIGMA, Q0, 1, 6, -1.0, solver="direct")
     refl = O.l1ra(QQ, I, None, Q0, 1, 2, 1e-9)
-    for sv in (0, 128):
+    for sv in (0, 256, 128):
         Q, w, info, Ql, il, Q1, i1 = res[sv]
         assert info.cg_hit_max == 0 and il.cg_hit_max == 0
         assert O.geodesic_rms(Q, ref.Q, 1) <= RMS_TOL
         assert np.allclose(w, ref.weights, rtol=1e-5, atol=1e-8)
         assert il.iters == refl.iters and O.geodesic_rms(Ql, refl.Q, 1) <= RMS_TOL
-    assert res[0][2].pcg_kernel == 7 and res[128][2].pcg_kernel in (2, 3)
+    assert res[0][2].pcg_kernel == 8 and res[256][2].pcg_kernel == 7 and res[128][2].pcg_kernel in (2, 3)
     assert res[0][6].pcg_kernel in (2, 3)                       # L1: stiff pairs need the exact blocks
-    print("PCG iterations, two-level vs one-level: irls", sum(res[0][2].cg_iters), sum(res[128][2].cg_iters),
-          "l1ra Newton", sum(res[0][4].cg_iters), sum(res[128][4].cg_iters))
-    assert sum(res[0][2].cg_iters) * 3 <= sum(res[128][2].cg_iters)
-    assert sum(res[0][4].cg_iters) * 2 <= sum(res[128][4].cg_iters)
+    print("PCG iterations, tridiagonal / dense two-level vs one-level: irls", sum(res[0][2].cg_iters), sum(res[256][2].cg_iters),
+          sum(res[128][2].cg_iters), "l1ra Newton", sum(res[0][4].cg_iters), sum(res[256][4].cg_iters), sum(res[128][4].cg_iters))
+    assert sum(res[256][2].cg_iters) * 3 <= sum(res[128][2].cg_iters)
+    assert sum(res[256][4].cg_iters) * 2 <= sum(res[128][4].cg_iters)
+    assert sum(res[0][2].cg_iters) <= sum(res[256][2].cg_iters)          # 2 500 views: 313 blocks against 64
+    assert sum(res[0][4].cg_iters) <= sum(res[256][4].cg_iters)
+
+
+def test_two_level_tridiagonal_dead_pivots(built_lib):
+    """Tridiagonal coarse operator on a graph whose partition has dead unknowns - a long all-fixed prefix leaves the
+    first five blocks of the partition empty (zero pivots, switched off): same rotations as the one-level kernels and
+    the oracle."""
+    import irotavg_b200 as ira
+    from oracle import rotavg_stream as RS
+    ops, Qgt = RS.make_stream(n_frames=1500, loop_every=400, min_loop_gap=300, sigma_n=0.01)
+    I = np.array([(op[1], op[2]) for op in ops if op[0] == "E"], dtype=np.int32)
+    QQ = np.array([O.rmat2quat(op[3]) for op in ops if op[0] == "E"])
+    rng = np.random.default_rng(9)
+    Q0 = O.quat_mult(Qgt, G._exp_quat(rng.normal(0, 0.05, (Qgt.shape[0], 3))))
+    f = 40                                                       # five whole blocks of 8 rows are fixed
+    Q0[:f] = Qgt[:f]
+    ref = O.irls(QQ, I, None, O.GEMAN_MCCLURE, SIGMA, Q0, f, 4, -1.0, solver="direct")
+    out = {}
+    for sv in (0, 128):
+        with ira.Solver(solver=sv) as s:
+            Q, w, info = s.irls(QQ, I, None, O.GEMAN_MCCLURE, SIGMA, Q0, f, 4, -1.0)
+        assert info.cg_hit_max == 0
+        assert O.geodesic_rms(Q, ref.Q, f) <= RMS_TOL
+        out[sv] = info
+    assert out[0].pcg_kernel == 8
+    assert sum(out[0].cg_iters) * 2 <= sum(out[128].cg_iters)

@@ -41,6 +41,12 @@ def run(frames=10000, loop_every=500, cpu_frames=150):
     ops, Qgt = RS.make_stream(n_frames=args.frames, loop_every=args.loop_every, min_loop_gap=min(500, args.loop_every))
     inp, outp = os.path.join(tmp, "ops.txt"), os.path.join(tmp, "out.txt")
     RS.write_ops(inp, ops)
+    san = os.environ.get("IRA_STREAM_SANITIZE")              # e.g. initcheck: replay under compute-sanitizer, print its report
+    if san:
+        r = subprocess.run(["compute-sanitizer", "--tool", san, "--print-limit", "30", exe, inp, outp], stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True)
+        print(r.stdout[-6000:])
+        return {"sanitize": san, "returncode": r.returncode}
     t0 = time.perf_counter()
     subprocess.run([exe, inp, outp], check=True)
     wall = time.perf_counter() - t0
@@ -57,16 +63,19 @@ def run(frames=10000, loop_every=500, cpu_frames=150):
         if v.size == 0:
             return None
         return {"calls": int(v.size), "p50_ms": float(np.percentile(v, 50)), "p99_ms": float(np.percentile(v, 99)),
-                "mean_ms": float(v.mean()), "max_vertices": int(calls[mask & solved, 2].max()),
+                "mean_ms": float(v.mean()), "max_ms": float(v.max()), "calls_over_1ms": int((v > 1.0).sum()),
+                "max_vertices": int(calls[mask & solved, 2].max()),
                 "max_edges": int(calls[mask & solved, 3].max())}
 
     Q = np.array([O.rmat2quat(r) for r in R])
+    import hashlib
+    result_sha1 = hashlib.sha1(np.ascontiguousarray(R).tobytes()).hexdigest()[:12]
     line = {"metric": "rotAvg window calls/s on a growing graph (config 5)", "value": float(solved.sum() / lat[solved].sum() * 1e3),
             "unit": "calls/s", "frames": args.frames, "loop_every": args.loop_every, "wall_s_incl_parsing": wall,
             "local": stats(~glob), "global": stats(glob),
             "global_calls": [{"views": int(c[2]), "edges": int(c[3]), "l1_iters": int(c[5]), "irls_iters": int(c[6]),
                               "ms": float(c[7] * 1e3)} for c in calls[glob & solved]],
-            "geodesic_rms_vs_ground_truth_rad": float(O.geodesic_rms(Q, Qgt, 1))}
+            "geodesic_rms_vs_ground_truth_rad": float(O.geodesic_rms(Q, Qgt, 1)), "result_sha1": result_sha1}
     # the reference's own CPU path on the same stream: oracle/_ref/rotavg_reference = the source text of
     # ViewGraph::rotAvg + ral/l1_irls.cpp compiled by oracle/build_ref.py (dense stand-in solvers: window-sized problems
     # only, so the prefix before the first global call)
