@@ -868,28 +868,8 @@ ira_status plan_slice_map(ira_context* h) {
   IRA_CUDA(h, cudaMemcpyAsync(h->h_slice_width.data(), h->slice_width.p, sizeof(int) * (size_t)h->nslices,
                               cudaMemcpyDeviceToHost, h->stream));
   IRA_CUDA(h, cudaStreamSynchronize(h->stream));
-  std::vector<int> order((size_t)h->nslices);
-  for (int s = 0; s < h->nslices; ++s) order[(size_t)s] = s;
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->h_slice_width[(size_t)a] > h->h_slice_width[(size_t)b]; });
-  std::vector<int64_t> load((size_t)grid, 0);
-  std::vector<int> used((size_t)grid, 0);
-  std::vector<int> map((size_t)grid * wpb, -1);
-  // (load, block) min-heap; ties broken by block index: deterministic
-  typedef std::pair<int64_t, int> Item;
-  std::vector<Item> heap;
-  for (int b = 0; b < grid; ++b) heap.push_back(Item(0, b));
-  auto cmp = [](const Item& a, const Item& b) { return a > b; };
-  std::make_heap(heap.begin(), heap.end(), cmp);
-  for (int s : order) {
-    std::pop_heap(heap.begin(), heap.end(), cmp);
-    Item it = heap.back();
-    heap.pop_back();
-    const int b = it.second;
-    map[(size_t)b * wpb + used[(size_t)b]] = s;
-    used[(size_t)b] += 1;
-    load[(size_t)b] += std::max(h->h_slice_width[(size_t)s], 1);
-    if (used[(size_t)b] < wpb) { heap.push_back(Item(load[(size_t)b], b)); std::push_heap(heap.begin(), heap.end(), cmp); }
-  }
+  std::vector<int> map;
+  plan::lpt_slice_map(h->h_slice_width.data(), h->nslices, grid, wpb, &map);
   IRA_CUDA(h, h->slice_map.reserve(sizeof(int) * map.size()));
   IRA_CUDA(h, cudaMemcpyAsync(h->slice_map.p, map.data(), sizeof(int) * map.size(), cudaMemcpyHostToDevice, h->stream));
   IRA_CUDA(h, cudaStreamSynchronize(h->stream));      // `map` is a local
@@ -905,20 +885,8 @@ ira_status plan_slice_map(ira_context* h) {
 // are lumped onto the diagonal of the coarse operator).  +256: dense 64-block variant only (A/B).
 void plan_coarse_tri(ira_context* h, const int32_t* I_pairs) {
   h->tri_bsz = 0;
-  const int n = h->n, nfree = h->n - h->f;
-  if ((h->opt.solver & (128 | 256)) || h->opt.lanes_per_row >= 2 || h->pcg_blocks_per_sm <= 0 || n > kCoarseMaxRows ||
-      nfree <= kTriMinBlock * kCoarseMax)
-    return;
-  for (int bsz = kTriMinBlock; bsz <= kSellC; bsz *= 2) {
-    if (cdiv(n, bsz) > kTriMax) continue;
-    if (cdiv(n, bsz) <= kCoarseMax) break;
-    int64_t far = 0;
-    for (int64_t k = 0; k < h->m; ++k) {
-      const int d = I_pairs[2 * k] / bsz - I_pairs[2 * k + 1] / bsz;
-      if (d > 1 || d < -1) ++far;
-    }
-    if (far * 50 <= h->m) { h->tri_bsz = bsz; return; }
-  }
+  if ((h->opt.solver & (128 | 256)) || h->opt.lanes_per_row >= 2 || h->pcg_blocks_per_sm <= 0) return;
+  h->tri_bsz = plan::tri_block_rows(h->n, h->f, h->m, I_pairs);
 }
 
 ira_status plan_coarse(ira_context* h, const int32_t* I_pairs) {
@@ -943,19 +911,8 @@ ira_status plan_coarse(ira_context* h, const int32_t* I_pairs) {
     }
     cudaGetLastError();
   }
-  const int bsz = std::max(2, cdiv(n, kCoarseMax));
-  const int nc = cdiv(n, bsz);
-  if (nc < 2 || nc > kCoarseMax) return IRA_OK;
-  // Is the graph a chain in its node numbering?  Long-range edges (loop closures) make a view graph an expander:
-  // config 2's 9 % of them leave one-level PCG at 64 iterations per solve and the two-level kernel, at 2.5x the cost
-  // per iteration, loses (measured 19.7 against 9.9 ms); a SLAM stream (0.05 %) or the reference's fixture (none) needs
-  // thousands of iterations without the coarse space.  Threshold: at most 2 % of the edges span more than two blocks.
-  int64_t far = 0;
-  for (int64_t k = 0; k < h->m; ++k) {
-    const int64_t d = (int64_t)I_pairs[2 * k] - (int64_t)I_pairs[2 * k + 1];
-    if ((d < 0 ? -d : d) > 2 * (int64_t)bsz) ++far;
-  }
-  if (far * 50 > h->m) return IRA_OK;
+  int bsz = 0, nc = 0;
+  if (!plan::dense_partition(n, h->f, h->m, I_pairs, &bsz, &nc)) return IRA_OK;   // chain-likeness test: ira_plan.hpp
   const int bytes = (int)sizeof(double) * (((3 * nc * nc + 3) & ~3) + 8 * nc);
   if (cudaFuncSetAttribute(k_pcg_coarse_w3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) { cudaGetLastError(); return IRA_OK; }
   int nb = 0;

@@ -40,14 +40,16 @@
 // restriction happens in registers: three grid barriers per iteration instead of four.
 #pragma once
 #include "ira_l1ra.cuh"
+#include "ira_plan.hpp"
 
 namespace ira {
 
-constexpr int kCoarseMax = 64;          // coarse unknowns per coordinate (3 x 64 x 64 doubles = 96 KB of shared memory)
+using plan::kCoarseMax;                 // coarse unknowns per coordinate, dense variant (ira_plan.hpp)
+using plan::kCoarseMaxRows;
+using plan::kTriMax;                    // tridiagonal variant
+using plan::kTriMinBlock;
 constexpr int kCoarseThreads = 384;     // >= kPcgNV warps: pcg_grid_reduce gives each of its 9 sums to one warp
-constexpr int kCoarseMaxRows = 32768;   // larger graphs keep the one-level kernels (148 x 12 warps hold 56 832 rows)
-constexpr int kTriMax = 1024;           // tridiagonal variant: coarse unknowns per coordinate (6 x 3 x 1024 doubles = 144 KB)
-constexpr int kTriMinBlock = 8;         // rows per block of the partition at least (the window edges must stay within adjacent blocks)
+static_assert(plan::kSellRows == kSellC, "ira_plan.hpp and the SELL kernels must agree on the slice height");
 
 struct PcgCoarseParams {
   PcgW3Params w;                        // matrix (3 weights per entry), vectors, partials, ctl
