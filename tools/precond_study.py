@@ -173,7 +173,74 @@ def coarse_study():
     test("config 2, unit weights", g.n, 1, g.I, np.ones(g.m))
 
 
+def coarse_tri_study(n=9500):
+    """The numbers behind the tridiagonal coarse operator (ira_coarse.cuh TRI) on a config-5 stream graph:
+    PCG iterations (rtol 1e-10, random right-hand sides) with Jacobi + piecewise-constant coarse space over nc
+    contiguous index blocks, the coarse operator P^T L P (a) solved exactly, (b) cut to its tridiagonal part with the far
+    couplings kept on the diagonal ("lump", what the kernel does) or removed from it ("drop"), (c) (b) plus the dense
+    64-block space, (d) a BPX-style multilevel sum of diagonally scaled levels above an exact 64-block level."""
+    from oracle import rotavg_stream as RS
+    ops, _ = RS.make_stream(n_frames=n, loop_every=500, min_loop_gap=500)
+    I = np.array([(op[1], op[2]) for op in ops if op[0] == "E"])
+    nf = n - 1
+
+    def P_of(bsz):
+        lab = np.arange(nf) // bsz
+        return sp.csr_matrix((np.ones(nf), (np.arange(nf), lab)), shape=(nf, lab.max() + 1))
+
+    def tri(L, d, nc, mode):
+        P = P_of(int(np.ceil(nf / nc)))
+        Ac = (P.T @ L @ P).tocoo()
+        near = np.abs(Ac.row - Ac.col) <= 1
+        T = sp.csc_matrix((Ac.data[near], (Ac.row[near], Ac.col[near])), shape=Ac.shape)
+        if mode == "drop":
+            far = ~near
+            T = T + sp.csc_matrix((Ac.data[far], (Ac.row[far], Ac.row[far])), shape=Ac.shape)
+        lu = spla.splu(T.tocsc())
+        return (lambda R: R / d[:, None] + P @ lu.solve(P.T @ R)), P.shape[1]
+
+    def multilevel(L, d, factor):
+        B = int(np.ceil(nf / 64))
+        Ps, Ds, b = [], [], factor
+        while b < B:
+            P = P_of(b)
+            Ps.append(P)
+            Ds.append((P.T @ L @ P).diagonal())
+            b *= factor
+        PL = P_of(B)
+        lu = spla.splu((PL.T @ L @ PL).tocsc())
+
+        def apply(R):
+            U = R / d[:, None]
+            for P, D in zip(Ps, Ds):
+                U = U + P @ ((P.T @ R) / D[:, None])
+            return U + PL @ lu.solve(PL.T @ R)
+        return apply
+
+    for wname, w2 in (("unit weights", np.ones(len(I))), ("weights 1e-2..1e2", 10 ** np.random.default_rng(1).uniform(-2, 2, len(I)))):
+        L, d = laplacian(n, 1, I, w2)
+        B = np.random.default_rng(0).standard_normal((nf, 3))
+        dj = lambda R: R / d[:, None]
+        out = {}
+        for nc in (64, 128, 256, 512, 1024):
+            M, ncc = coarse_additive(L, d, np.arange(nf) // int(np.ceil(nf / nc)), dj, exact=True)
+            out[f"exact{ncc}"] = pcg(L, B, M, max_iters=20000)[1]
+        for nc in (64, 256, 512, 1024, 2048):
+            for mode in ("lump", "drop"):
+                M, ncc = tri(L, d, nc, mode)
+                out[f"tri{ncc}{mode}"] = pcg(L, B, M, max_iters=20000)[1]
+        for nc in (512, 1024):
+            M1, ncc = tri(L, d, nc, "lump")
+            M2, _ = coarse_additive(L, d, np.arange(nf) // int(np.ceil(nf / 64)), lambda R: 0 * R, exact=True)
+            out[f"tri{ncc}lump+dense64"] = pcg(L, B, lambda R: M1(R) + M2(R), max_iters=20000)[1]
+        for factor in (2, 4, 8):
+            out[f"multilevel x{factor}"] = pcg(L, B, multilevel(L, d, factor), max_iters=20000)[1]
+        print(f"stream, {n} views, {wname}:", out, flush=True)
+
+
 def main():
+    if "--coarse-tri" in sys.argv:
+        return coarse_tri_study()
     if "--coarse" in sys.argv:
         return coarse_study()
     ap = argparse.ArgumentParser()
