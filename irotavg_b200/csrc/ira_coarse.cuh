@@ -28,8 +28,8 @@
 // fewer iterations.
 //
 // Tridiagonal variant (TRI, graphs of more than ~500 free nodes).  With 64 blocks the iteration count still grows like
-// the block length (numpy, 9 500-view stream graph, unit weights: 366 iterations with 64 blocks, 108 with 250, 41 with
-// 950).  For CONTIGUOUS index blocks P^T L P is tridiagonal up to the loop closures, and keeping only its tridiagonal
+// the block length (tools/precond_study.py --coarse-tri: 9 500-view stream graph, unit weights: 366 iterations with 64
+// blocks, 108 with 250, 41 with 950).  For CONTIGUOUS index blocks P^T L P is tridiagonal up to the loop closures, and keeping only its tridiagonal
 // part T (the far couplings stay on the diagonal: T is diagonally dominant, SPD) costs little: 138 / 96 / 78 / 65
 // iterations with 250 / 500 / 950 / 1 900 blocks, the same again with the dense 64-block space added on top.  So
 // nc grows to <= 1 024 blocks of >= 8 rows, and every thread block solves T y = r_c by cyclic reduction in its shared
